@@ -1,0 +1,448 @@
+// fsb_capi.cu -- runtime, handle management and the product entry points of the C ABI
+// (include/fsb.h).  No CPU fallback: every compute entry point starts with
+// fsb_require_device() and fails with FSB_ENODEV when no CUDA device is usable.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "fsb_internal.h"
+
+namespace {
+thread_local char tl_error[512] = "";
+std::mutex g_init_mu;
+bool g_inited = false;
+int g_device = -1;
+cudaStream_t g_stream = nullptr;
+cudaStream_t g_copy_stream = nullptr;
+std::atomic<long> g_launches{0};
+}  // namespace
+
+int fsb_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof tl_error, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line) {
+  const char* base = strrchr(file, '/');
+  return fsb_set_error(e == cudaErrorMemoryAllocation ? FSB_ENOMEM : FSB_ECUDA, "CUDA error %d (%s) in %s at %s:%d",
+                       (int)e, cudaGetErrorString(e), what, base ? base + 1 : file, line);
+}
+
+void fsb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+cudaStream_t fsb_default_stream() { return g_stream; }
+
+int fsb_require_device() {
+  if (g_inited) return FSB_OK;
+  return fsb_init(-1);
+}
+
+extern "C" {
+
+int fsb_version(void) { return 100; }
+const char* fsb_last_error(void) { return tl_error; }
+long fsb_launch_count(void) { return g_launches.load(); }
+
+int fsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fsb_init(int device) {
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  int n = fsb_device_count();
+  if (n <= 0) return fsb_set_error(FSB_ENODEV, "no CUDA device: libfastsparse_b200 has no CPU fallback");
+  if (g_inited && (device < 0 || device == g_device)) return FSB_OK;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= n) return fsb_set_error(FSB_EINVAL, "fsb_init: device %d out of range (%d visible)", device, n);
+  FSB_CUDA(cudaSetDevice(device));
+  if (g_inited) {  // re-bind to another device: drop the old streams
+    cudaStreamDestroy(g_stream);
+    cudaStreamDestroy(g_copy_stream);
+    g_inited = false;
+  }
+  FSB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  FSB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+  g_device = device;
+  g_inited = true;
+  return FSB_OK;
+}
+
+int fsb_sync(void) {
+  FSB_TRY(fsb_require_device());
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
+void* fsb_stream(void) { return (void*)g_stream; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ handles
+int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out) {
+  if (bytes > A->tmp_cap) {
+    if (A->tmp) cudaFree(A->tmp);
+    A->tmp = nullptr;
+    A->tmp_cap = 0;
+    FSB_CUDA(cudaMalloc(&A->tmp, bytes));
+    A->tmp_cap = bytes;
+  }
+  *out = A->tmp;
+  return FSB_OK;
+}
+
+static void free_arrays(fsb_matrix* A) {
+  if (!A) return;
+  cudaFree(A->row_ptr); cudaFree(A->cols); cudaFree(A->vals);
+  cudaFree(A->start_row); cudaFree(A->blk_off); cudaFree(A->b_rows); cudaFree(A->b_cols); cudaFree(A->b_vals);
+  cudaFree(A->tmp);
+  if (A->T) { free_arrays(A->T); delete A->T; }
+}
+
+template <typename T>
+static int upload_array(T** dst, const T* src, size_t n, cudaStream_t st) {
+  FSB_CUDA(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) FSB_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  return FSB_OK;
+}
+
+extern "C" {
+
+int fsb_csr_upload(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* row_ptr, const int* cols, const double* vals) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow < 0 || ncol < 0 || nnz < 0 || !row_ptr || (nnz > 0 && !cols)) return fsb_set_error(FSB_EINVAL, "fsb_csr_upload: bad arguments");
+  if (row_ptr[nrow] != nnz) return fsb_set_error(FSB_EINVAL, "fsb_csr_upload: row_ptr[nrow]=%d but nnz=%ld", row_ptr[nrow], nnz);
+  fsb_matrix* A = new fsb_matrix();
+  A->format = FSB_FMT_CSR; A->nrow = nrow; A->ncol = ncol; A->nnz = nnz; A->has_vals = vals != nullptr;
+  A->avg_row_nnz = nrow > 0 ? (double)nnz / nrow : 0.0;
+  int rc = upload_array(&A->row_ptr, row_ptr, (size_t)nrow + 1, g_stream);
+  if (rc == FSB_OK) rc = upload_array(&A->cols, cols, (size_t)nnz, g_stream);
+  if (rc == FSB_OK && vals) rc = upload_array(&A->vals, vals, (size_t)nnz, g_stream);
+  if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
+  if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
+  A->bytes = ((size_t)nrow + 1) * 4 + (size_t)nnz * (vals ? 12 : 4);
+  *out = A;
+  return FSB_OK;
+}
+
+int fsb_csr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows, const int* d_cols, const double* d_vals) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow < 0 || ncol < 0 || nnz < 0 || (nnz > 0 && (!d_rows || !d_cols))) return fsb_set_error(FSB_EINVAL, "fsb_csr_from_coo_dev: bad arguments");
+  fsb_matrix* A = new fsb_matrix();
+  int rc = fsb_build_csr_from_coo_dev(A, nrow, ncol, nnz, d_rows, d_cols, d_vals, g_stream);
+  if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
+  *out = A;
+  return FSB_OK;
+}
+
+int fsb_csr_upload_coo(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* rows, const int* cols, const double* vals) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow < 0 || ncol < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols))) return fsb_set_error(FSB_EINVAL, "fsb_csr_upload_coo: bad arguments");
+  int *dr = nullptr, *dc = nullptr;
+  double* dv = nullptr;
+  int rc = upload_array(&dr, rows, (size_t)nnz, g_stream);
+  if (rc == FSB_OK) rc = upload_array(&dc, cols, (size_t)nnz, g_stream);
+  if (rc == FSB_OK && vals) rc = upload_array(&dv, vals, (size_t)nnz, g_stream);
+  if (rc == FSB_OK) rc = fsb_csr_from_coo_dev(out, nrow, ncol, nnz, dr, dc, dv);
+  cudaFree(dr); cudaFree(dc); cudaFree(dv);
+  return rc;
+}
+
+int fsb_cbcsr_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, int colblocksize, long nnz, const int* row_ptr, const int* cols) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow < 0 || ncol < 0 || nblocks < 0 || colblocksize <= 0 || nnz < 0 || !row_ptr) return fsb_set_error(FSB_EINVAL, "fsb_cbcsr_upload: bad arguments");
+  const size_t ncell = (size_t)nblocks * nrow;
+  if (row_ptr[ncell] != nnz) return fsb_set_error(FSB_EINVAL, "fsb_cbcsr_upload: row_ptr[last]=%d but nnz=%ld", row_ptr[ncell], nnz);
+  fsb_matrix* A = new fsb_matrix();
+  A->format = FSB_FMT_CBCSR; A->nrow = nrow; A->ncol = ncol; A->nnz = nnz;
+  A->nblocks = nblocks; A->colblocksize = colblocksize;
+  A->avg_row_nnz = nrow > 0 ? (double)nnz / nrow : 0.0;
+  int rc = upload_array(&A->row_ptr, row_ptr, ncell + 1, g_stream);
+  if (rc == FSB_OK) rc = upload_array(&A->cols, cols, (size_t)nnz, g_stream);
+  if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
+  if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
+  A->bytes = (ncell + 1) * 4 + (size_t)nnz * 4;
+  *out = A;
+  return FSB_OK;
+}
+
+int fsb_blocked_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, const int* start_row, const int* blk_nnz,
+                       int* const* rows, int* const* cols, double* const* vals) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow < 0 || ncol < 0 || nblocks < 0 || !start_row || (nblocks > 0 && (!blk_nnz || !rows || !cols)))
+    return fsb_set_error(FSB_EINVAL, "fsb_blocked_upload: bad arguments");
+  fsb_matrix* A = new fsb_matrix();
+  A->format = FSB_FMT_BLOCKED; A->nrow = nrow; A->ncol = ncol; A->nblocks = nblocks; A->has_vals = vals != nullptr;
+  std::vector<long> off((size_t)nblocks + 1, 0);
+  for (int b = 0; b < nblocks; ++b) {
+    off[b + 1] = off[b] + blk_nnz[b];
+    A->max_block_rows = std::max(A->max_block_rows, start_row[b + 1] - start_row[b]);
+  }
+  A->nnz = off[nblocks];
+  A->avg_row_nnz = nrow > 0 ? (double)A->nnz / nrow : 0.0;
+  const size_t n1 = std::max<size_t>((size_t)A->nnz, 1);
+  int rc = upload_array(&A->start_row, start_row, (size_t)nblocks + 1, g_stream);
+  if (rc == FSB_OK) rc = upload_array(&A->blk_off, off.data(), (size_t)nblocks + 1, g_stream);
+  auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess ? FSB_OK : fsb_cuda_error(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__); };
+  if (rc == FSB_OK) rc = alloc((void**)&A->b_rows, n1 * 4);
+  if (rc == FSB_OK) rc = alloc((void**)&A->b_cols, n1 * 4);
+  if (rc == FSB_OK && vals) rc = alloc((void**)&A->b_vals, n1 * 8);
+  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
+    const size_t m = (size_t)blk_nnz[b];
+    if (!m) continue;
+    cudaError_t e = cudaMemcpyAsync(A->b_rows + off[b], rows[b], m * 4, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(A->b_cols + off[b], cols[b], m * 4, cudaMemcpyHostToDevice, g_stream);
+    if (e == cudaSuccess && vals) e = cudaMemcpyAsync(A->b_vals + off[b], vals[b], m * 8, cudaMemcpyHostToDevice, g_stream);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "blocked upload", __FILE__, __LINE__);
+  }
+  if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
+  A->bytes = ((size_t)nblocks + 1) * 12 + n1 * (vals ? 16 : 8);
+  if (rc == FSB_OK) rc = fsb_blocked_relayout(A, g_stream);
+  if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
+  *out = A;
+  return FSB_OK;
+}
+
+int fsb_matrix_free(fsb_matrix_t A) {
+  if (!A) return FSB_OK;
+  free_arrays(A);
+  delete A;
+  return FSB_OK;
+}
+
+int fsb_matrix_info(fsb_matrix_t A, int* format, int* nrow, int* ncol, long* nnz, int* has_vals, int* nblocks) {
+  if (!A) return fsb_set_error(FSB_EINVAL, "null handle");
+  if (format) *format = A->format;
+  if (nrow) *nrow = A->nrow;
+  if (ncol) *ncol = A->ncol;
+  if (nnz) *nnz = A->nnz;
+  if (has_vals) *has_vals = A->has_vals;
+  if (nblocks) *nblocks = A->nblocks;
+  return FSB_OK;
+}
+
+long fsb_matrix_bytes(fsb_matrix_t A) {
+  if (!A) return 0;
+  return (long)(A->bytes + (A->T ? A->T->bytes : 0) + A->tmp_cap);
+}
+
+int fsb_matrix_set_row_sharded(fsb_matrix_t A, int sharded) {
+  if (!A) return fsb_set_error(FSB_EINVAL, "null handle");
+  A->sharded = sharded != 0;
+  return FSB_OK;
+}
+
+int fsb_csr_download(fsb_matrix_t A, int* row_ptr, int* cols, double* vals) {
+  FSB_TRY(fsb_require_device());
+  if (!A || A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_csr_download: CSR handle required");
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  if (row_ptr) FSB_CUDA(cudaMemcpy(row_ptr, A->row_ptr, ((size_t)A->nrow + 1) * 4, cudaMemcpyDeviceToHost));
+  if (cols && A->nnz) FSB_CUDA(cudaMemcpy(cols, A->cols, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost));
+  if (vals && A->nnz) {
+    if (!A->has_vals) return fsb_set_error(FSB_EINVAL, "fsb_csr_download: binary matrix has no values");
+    FSB_CUDA(cudaMemcpy(vals, A->vals, (size_t)A->nnz * 8, cudaMemcpyDeviceToHost));
+  }
+  return FSB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void rebase_kernel(int* __restrict__ out, const int* __restrict__ in, int n, int base) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[i] - base;
+}
+}  // namespace
+
+extern "C" int fsb_csr_row_slice(fsb_matrix_t* out, fsb_matrix_t A, int r0, int r1) {
+  FSB_TRY(fsb_require_device());
+  if (!out || !A || A->format != FSB_FMT_CSR || r0 < 0 || r1 < r0 || r1 > A->nrow) return fsb_set_error(FSB_EINVAL, "fsb_csr_row_slice: bad arguments");
+  int ends[2] = {0, 0};
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  FSB_CUDA(cudaMemcpy(&ends[0], A->row_ptr + r0, 4, cudaMemcpyDeviceToHost));
+  FSB_CUDA(cudaMemcpy(&ends[1], A->row_ptr + r1, 4, cudaMemcpyDeviceToHost));
+  const long nnz = (long)ends[1] - ends[0];
+  fsb_matrix* S = new fsb_matrix();
+  S->format = FSB_FMT_CSR; S->nrow = r1 - r0; S->ncol = A->ncol; S->nnz = nnz; S->has_vals = A->has_vals;
+  S->avg_row_nnz = S->nrow > 0 ? (double)nnz / S->nrow : 0.0;
+  const size_t n1 = std::max<size_t>((size_t)nnz, 1);
+  cudaError_t e = cudaMalloc(&S->row_ptr, ((size_t)S->nrow + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&S->cols, n1 * 4);
+  if (e == cudaSuccess && A->has_vals) e = cudaMalloc(&S->vals, n1 * 8);
+  if (e == cudaSuccess) {
+    rebase_kernel<<<std::min(148 * 8, (S->nrow + 256) / 256), 256, 0, g_stream>>>(S->row_ptr, A->row_ptr + r0, S->nrow + 1, ends[0]);
+    fsb_count_launch();
+    if (nnz) e = cudaMemcpyAsync(S->cols, A->cols + ends[0], (size_t)nnz * 4, cudaMemcpyDeviceToDevice, g_stream);
+    if (e == cudaSuccess && nnz && A->has_vals) e = cudaMemcpyAsync(S->vals, A->vals + ends[0], (size_t)nnz * 8, cudaMemcpyDeviceToDevice, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+  }
+  if (e != cudaSuccess) { free_arrays(S); delete S; return fsb_cuda_error(e, "fsb_csr_row_slice", __FILE__, __LINE__); }
+  S->bytes = ((size_t)S->nrow + 1) * 4 + n1 * (A->has_vals ? 12 : 4);
+  *out = S;
+  return FSB_OK;
+}
+
+// ------------------------------------------------------------------ products
+static int spmm_any(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+  switch (A->format) {
+    case FSB_FMT_CSR: return fsb_launch_csr_spmm(A, dY, dX, R, st);
+    case FSB_FMT_CBCSR: return fsb_launch_cbcsr_spmm(A, dY, dX, R, st);
+    case FSB_FMT_BLOCKED: return fsb_launch_blocked_spmm(A, dY, dX, R, st);
+  }
+  return fsb_set_error(FSB_EINVAL, "unknown matrix format %d", A->format);
+}
+
+// allreduce of a row shard's partial A'(...); no-op without a communicator
+static int maybe_allreduce(fsb_matrix* A, double* dY, long count, cudaStream_t st) {
+  if (A->sharded && fsb_comm_active()) return fsb_allreduce_sum_dev(dY, count, (void*)st);
+  return FSB_OK;
+}
+
+extern "C" {
+
+int fsb_spmm_dev(fsb_matrix_t A, double* dY, const double* dX, int R, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !dY || !dX) return fsb_set_error(FSB_EINVAL, "fsb_spmm_dev: null argument");
+  return spmm_any(A, dY, dX, R, fsb_pick_stream(stream));
+}
+
+int fsb_spmm_t_dev(fsb_matrix_t A, double* dY, const double* dX, int R, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !dY || !dX) return fsb_set_error(FSB_EINVAL, "fsb_spmm_t_dev: null argument");
+  if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_spmm_t_dev: CSR handle required (pass the stored transpose for blocked formats)");
+  cudaStream_t st = fsb_pick_stream(stream);
+  FSB_TRY(fsb_build_transpose(A, st));
+  FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dX, R, st));
+  return maybe_allreduce(A, dY, (long)A->ncol * R, st);
+}
+
+int fsb_ata_dev(fsb_matrix_t A, double* dY, const double* dX, int R, double lambda, double* dTmp, int mode, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !dY || !dX) return fsb_set_error(FSB_EINVAL, "fsb_ata_dev: null argument");
+  if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_ata_dev: CSR handle required");
+  cudaStream_t st = fsb_pick_stream(stream);
+  const long nF = (long)A->ncol * R;
+  const bool dist = A->sharded && fsb_comm_active();
+  if (mode == 1) {
+    // lambda*X is added once: by rank 0 only when partials are summed across ranks
+    const double lam = (dist && fsb_comm_rank() != 0) ? 0.0 : lambda;
+    FSB_TRY(fsb_launch_csr_ata_fused(A, dY, dX, R, lam, st));
+    return maybe_allreduce(A, dY, nF, st);
+  }
+  if (!dTmp) FSB_TRY(fsb_matrix_scratch(A, (size_t)A->nrow * R * sizeof(double), &dTmp));
+  FSB_TRY(fsb_build_transpose(A, st));
+  FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
+  FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dTmp, R, st));
+  FSB_TRY(maybe_allreduce(A, dY, nF, st));
+  if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));
+  return FSB_OK;
+}
+
+int fsb_ata_pair_dev(fsb_matrix_t A, fsb_matrix_t At, double* dY, const double* dX, int R, double lambda, double* dTmp, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !At || !dY || !dX) return fsb_set_error(FSB_EINVAL, "fsb_ata_pair_dev: null argument");
+  if (A->nrow != At->ncol || A->ncol != At->nrow)
+    return fsb_set_error(FSB_EINVAL, "A (%d x %d) and At (%d x %d) must be transposes of each other.", A->nrow, A->ncol, At->nrow, At->ncol);
+  cudaStream_t st = fsb_pick_stream(stream);
+  if (!dTmp) FSB_TRY(fsb_matrix_scratch(A, (size_t)A->nrow * R * sizeof(double), &dTmp));
+  FSB_TRY(spmm_any(A, dTmp, dX, R, st));
+  FSB_TRY(spmm_any(At, dY, dTmp, R, st));
+  FSB_TRY(maybe_allreduce(A, dY, (long)A->ncol * R, st));
+  if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, (long)A->ncol * R, st));
+  return FSB_OK;
+}
+
+}  // extern "C"
+
+// ---- host-pointer products: stage X in, run, stage Y out.  Large outputs are
+// produced in row chunks so the D2H copy of chunk i overlaps the kernel of chunk i+1.
+namespace {
+
+struct HostStage {
+  double* dX = nullptr; size_t capX = 0;
+  double* dY = nullptr; size_t capY = 0;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+};
+HostStage g_stage;
+std::mutex g_stage_mu;
+
+int stage_reserve(size_t bx, size_t by) {
+  if (bx > g_stage.capX) {
+    cudaFree(g_stage.dX); g_stage.dX = nullptr; g_stage.capX = 0;
+    FSB_CUDA(cudaMalloc(&g_stage.dX, bx)); g_stage.capX = bx;
+  }
+  if (by > g_stage.capY) {
+    cudaFree(g_stage.dY); g_stage.dY = nullptr; g_stage.capY = 0;
+    FSB_CUDA(cudaMalloc(&g_stage.dY, by)); g_stage.capY = by;
+  }
+  if (!g_stage.ev[0]) {
+    FSB_CUDA(cudaEventCreateWithFlags(&g_stage.ev[0], cudaEventDisableTiming));
+    FSB_CUDA(cudaEventCreateWithFlags(&g_stage.ev[1], cudaEventDisableTiming));
+  }
+  return FSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_spmm_host: bad argument");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  const size_t bx = (size_t)A->ncol * R * 8, by = (size_t)A->nrow * R * 8;
+  FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
+  if (bx) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, bx, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(spmm_any(A, g_stage.dY, g_stage.dX, R, g_stream));
+  if (by) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, by, cudaMemcpyDeviceToHost, g_stream));
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
+int fsb_spmm_t_host(fsb_matrix_t A, double* Y, const double* X, int R) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_spmm_t_host: bad argument");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  const size_t bx = (size_t)A->nrow * R * 8, by = (size_t)A->ncol * R * 8;
+  FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
+  if (bx) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, bx, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_spmm_t_dev(A, g_stage.dY, g_stage.dX, R, g_stream));
+  if (by) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, by, cudaMemcpyDeviceToHost, g_stream));
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
+int fsb_ata_host(fsb_matrix_t A, double* Y, const double* X, int R, double lambda, int mode) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_ata_host: bad argument");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  const size_t b = (size_t)A->ncol * R * 8;
+  FSB_TRY(stage_reserve(std::max<size_t>(b, 8), std::max<size_t>(b, 8)));
+  if (b) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, b, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_ata_dev(A, g_stage.dY, g_stage.dX, R, lambda, nullptr, mode, g_stream));
+  if (b) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, b, cudaMemcpyDeviceToHost, g_stream));
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
+void fsb_die(const char* where) {
+  fprintf(stderr, "libfastsparse_b200: %s: %s\n", where ? where : "error", tl_error);
+  exit(1);
+}
+
+}  // extern "C"

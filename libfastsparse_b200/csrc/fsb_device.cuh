@@ -1,0 +1,82 @@
+// fsb_device.cuh -- device-side load/store helpers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fsbdev {
+
+// streaming int load: matrix indices are read exactly once per product
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int4 ld_stream_s32x4(const int* p) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// gather of VEC consecutive doubles of a dense operand row (read-only path).
+// VEC = 4 is one 256-bit LDG (sm_100+); the L2::evict_last form keeps the dense
+// operand resident in L2 against the streaming matrix/Y traffic.
+template <int VEC> struct XLoad;
+template <> struct XLoad<1> {
+  static __device__ __forceinline__ void ld(double* v, const double* p) {
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v[0]) : "l"(p));
+  }
+};
+template <> struct XLoad<2> {
+  static __device__ __forceinline__ void ld(double* v, const double* p) {
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  }
+};
+template <> struct XLoad<4> {
+  static __device__ __forceinline__ void ld(double* v, const double* p) {
+    asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+  }
+};
+
+// streaming (evict-first) store of VEC doubles: outputs are written once
+template <int VEC> struct YStore;
+template <> struct YStore<1> {
+  static __device__ __forceinline__ void st(double* p, const double* v) {
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v[0]) : "memory");
+  }
+};
+template <> struct YStore<2> {
+  static __device__ __forceinline__ void st(double* p, const double* v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+  }
+};
+template <> struct YStore<4> {
+  static __device__ __forceinline__ void st(double* p, const double* v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p + 2), "d"(v[2]), "d"(v[3]) : "memory");
+  }
+};
+
+// fire-and-forget fp64 add at L2 (REDG.E.ADD.F64)
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ double shfl_f64(unsigned mask, double v, int src, int width) {
+  return __shfl_sync(mask, v, src, width);
+}
+__device__ __forceinline__ double shfl_xor_f64(unsigned mask, double v, int off, int width) {
+  return __shfl_xor_sync(mask, v, off, width);
+}
+
+}  // namespace fsbdev

@@ -1,0 +1,94 @@
+// fsb_internal.h -- shared declarations of libfastsparse_b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/fsb.h"
+
+// Device-resident sparse matrix.  One struct for the three storage formats of the
+// reference; unused fields are null.  Everything here lives in HBM.
+struct fsb_matrix {
+  int format = 0;
+  int nrow = 0, ncol = 0;
+  long nnz = 0;
+  bool has_vals = false;
+  bool sharded = false;       // rows are one rank's shard: A'(...) partials get allreduced
+  // CSR / CBCSR (CBCSR: row_ptr has nblocks*nrow+1 entries)
+  int* row_ptr = nullptr;
+  int* cols = nullptr;
+  double* vals = nullptr;
+  int nblocks = 0, colblocksize = 0;
+  // BLOCKED (row-blocked COO, flattened; entries keep the host order per block)
+  int* start_row = nullptr;   // nblocks+1
+  long* blk_off = nullptr;    // nblocks+1
+  int* b_rows = nullptr;      // global row ids
+  int* b_cols = nullptr;
+  double* b_vals = nullptr;
+  int max_block_rows = 0;
+  // lazily built, cached transpose (CSR handles only)
+  fsb_matrix* T = nullptr;
+  // library-owned scratch (A X intermediate of A'A, host staging)
+  double* tmp = nullptr;
+  size_t tmp_cap = 0;
+  size_t bytes = 0;
+  double avg_row_nnz = 0.0;
+};
+
+// ---- error plumbing (fsb_runtime.cu)
+int fsb_set_error(int code, const char* fmt, ...);
+int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+int fsb_require_device();
+cudaStream_t fsb_default_stream();
+void fsb_count_launch(int n = 1);
+
+#define FSB_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return fsb_cuda_error(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define FSB_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != FSB_OK) return rc__; \
+  } while (0)
+
+#define FSB_KERNEL_CHECK()       \
+  do {                           \
+    fsb_count_launch();          \
+    FSB_CUDA(cudaGetLastError()); \
+  } while (0)
+
+static inline cudaStream_t fsb_pick_stream(void* s) {
+  return s ? (cudaStream_t)s : fsb_default_stream();
+}
+
+// ---- device scratch owned by a handle
+int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out);
+
+// ---- kernels_csr.cu
+int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st);
+// tuning override for the sweep tool: TW, G, VEC, slabs (0 = heuristic)
+void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
+
+// ---- kernels_cbcsr.cu / kernels_blocked.cu
+int fsb_launch_cbcsr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+int fsb_launch_blocked_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+
+// ---- kernels_build.cu
+int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
+                               const int* d_cols, const double* d_vals, cudaStream_t st);
+int fsb_build_transpose(fsb_matrix* A, cudaStream_t st);   // fills A->T
+int fsb_stable_perm_by_key(const int* d_keys, int nkeys, long n, int* d_perm, int* d_ptr, cudaStream_t st);
+#define FSB_BLOCKED_CLASSES 256
+int fsb_blocked_relayout(fsb_matrix* A, cudaStream_t st);  // bucket entries by row class; fills A->row_ptr
+
+// ---- kernels_dense.cu (CG building blocks)
+int fsb_dense_gram(double* dG, const double* dXa, const double* dXb, long n, int R, cudaStream_t st);
+int fsb_dense_axpy_lambda(double* dY, const double* dX, double lambda, long n, cudaStream_t st); // Y += lambda X
+
+// ---- fsb_comm.cu
+bool fsb_comm_active();

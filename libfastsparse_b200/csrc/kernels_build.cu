@@ -1,0 +1,274 @@
+// kernels_build.cu -- device-side structure construction and synthetic inputs.
+//
+// (1) COO -> CSR on the device by a STABLE radix sort on the row index.  The
+//     reference's new_bcsr / new_csr (csr.h:30-67, 375-422) is a stable counting
+//     sort, so the result (row_ptr, in-row order, duplicates) is bit-identical.
+//     This is construction, not the hot path: the sort itself is cub::DeviceRadixSort.
+// (2) CSR transpose (the reference obtains A' products by building a second CSR of
+//     the transposed COO: bench_a_mul_b.c:273-274, test_sparse.c:564-565).
+// (3) Counter-based synthetic COO generator shared bit-for-bit with the host
+//     (SURVEY 8d): entry j is a pure function of (seed, j).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "fsb_internal.h"
+#include "fsb_synth.h"
+
+namespace {
+
+__global__ void iota_kernel(int* p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = (int)i;
+}
+
+// row_ptr from the sorted key stream: position j opens every row in (key[j-1], key[j]]
+__global__ void row_ptr_from_sorted_kernel(const int* __restrict__ keys, long long n, int nrow, int* __restrict__ row_ptr) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j <= n; j += stride) {
+    const int lo = (j == 0) ? -1 : keys[j - 1];
+    const int hi = (j == n) ? nrow : keys[j];
+    for (int q = lo + 1; q <= hi; ++q) row_ptr[q] = (int)j;
+  }
+}
+
+__global__ void gather_i32_kernel(int* __restrict__ out, const int* __restrict__ in, const int* __restrict__ perm, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[perm[i]];
+}
+__global__ void gather_f64_kernel(double* __restrict__ out, const double* __restrict__ in, const int* __restrict__ perm, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = in[perm[i]];
+}
+
+// row id of every stored entry of a CSR (binary search in row_ptr)
+__global__ void expand_rows_kernel(const int* __restrict__ row_ptr, int nrow, long long nnz, int* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    int lo = 0, hi = nrow;  // largest r with row_ptr[r] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    out[i] = lo;
+  }
+}
+
+__global__ void synth_kernel(unsigned long long seed, int dist, long long nnz, int nrow, int ncol,
+                             int* __restrict__ rows, int* __restrict__ cols, double* __restrict__ vals) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j < nnz; j += stride) {
+    rows[j] = fsb_synth_row(seed, (unsigned long long)j, nrow);
+    cols[j] = fsb_synth_col(seed, (unsigned long long)j, ncol, dist);
+    if (vals) vals[j] = fsb_synth_val(seed, (unsigned long long)j);
+  }
+}
+
+inline int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148LL * 32); }
+
+int bits_for(int n) { int b = 1; while (b < 31 && (1LL << b) < n) ++b; return b; }
+
+}  // namespace
+
+// Sort (key, payload...) stably by key in [0, nkeys) and emit CSR arrays.
+static int coo_to_csr_dev(fsb_matrix* out, int nkeys, int nother, long nnz, const int* d_keys,
+                          const int* d_other, const double* d_vals, cudaStream_t st) {
+  out->format = FSB_FMT_CSR;
+  out->nrow = nkeys;
+  out->ncol = nother;
+  out->nnz = nnz;
+  out->has_vals = d_vals != nullptr;
+  out->avg_row_nnz = nkeys > 0 ? (double)nnz / nkeys : 0.0;
+  const size_t n1 = (size_t)std::max<long>(nnz, 1);
+  FSB_CUDA(cudaMalloc(&out->row_ptr, ((size_t)nkeys + 1) * sizeof(int)));
+  FSB_CUDA(cudaMalloc(&out->cols, n1 * sizeof(int)));
+  if (d_vals) FSB_CUDA(cudaMalloc(&out->vals, n1 * sizeof(double)));
+  out->bytes = ((size_t)nkeys + 1) * sizeof(int) + n1 * sizeof(int) + (d_vals ? n1 * sizeof(double) : 0);
+  if (nnz == 0) {
+    FSB_CUDA(cudaMemsetAsync(out->row_ptr, 0, ((size_t)nkeys + 1) * sizeof(int), st));
+    return FSB_OK;
+  }
+  int *keys_sorted = nullptr, *perm_in = nullptr, *perm_out = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  FSB_CUDA(cudaMalloc(&keys_sorted, n1 * sizeof(int)));
+  const int end_bit = bits_for(nkeys);
+  int rc = FSB_OK;
+  if (!d_vals) {
+    // payload = the other index itself
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, keys_sorted, d_other, out->cols, (long long)nnz, 0, end_bit, st);
+    FSB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, keys_sorted, d_other, out->cols, (long long)nnz, 0, end_bit, st);
+    fsb_count_launch(4);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "cub::DeviceRadixSort::SortPairs", __FILE__, __LINE__);
+  } else {
+    FSB_CUDA(cudaMalloc(&perm_in, n1 * sizeof(int)));
+    FSB_CUDA(cudaMalloc(&perm_out, n1 * sizeof(int)));
+    iota_kernel<<<grid_for(nnz), 256, 0, st>>>(perm_in, nnz);
+    fsb_count_launch();
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, keys_sorted, perm_in, perm_out, (long long)nnz, 0, end_bit, st);
+    FSB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, keys_sorted, perm_in, perm_out, (long long)nnz, 0, end_bit, st);
+    fsb_count_launch(4);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "cub::DeviceRadixSort::SortPairs", __FILE__, __LINE__);
+    if (rc == FSB_OK) {
+      gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(out->cols, d_other, perm_out, nnz);
+      gather_f64_kernel<<<grid_for(nnz), 256, 0, st>>>(out->vals, d_vals, perm_out, nnz);
+      fsb_count_launch(2);
+    }
+  }
+  if (rc == FSB_OK) {
+    row_ptr_from_sorted_kernel<<<grid_for(nnz + 1), 256, 0, st>>>(keys_sorted, nnz, nkeys, out->row_ptr);
+    fsb_count_launch();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "coo_to_csr_dev", __FILE__, __LINE__);
+  }
+  cudaFree(keys_sorted); cudaFree(perm_in); cudaFree(perm_out); cudaFree(tmp);
+  return rc;
+}
+
+// perm = indices 0..n-1 stably sorted by key (keys in [0, nkeys)); ptr[k] = first sorted position of key k
+int fsb_stable_perm_by_key(const int* d_keys, int nkeys, long n, int* d_perm, int* d_ptr, cudaStream_t st) {
+  if (n == 0) {
+    FSB_CUDA(cudaMemsetAsync(d_ptr, 0, ((size_t)nkeys + 1) * sizeof(int), st));
+    return FSB_OK;
+  }
+  int *keys_sorted = nullptr, *iota = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  FSB_CUDA(cudaMalloc(&keys_sorted, (size_t)n * sizeof(int)));
+  cudaError_t e = cudaMalloc(&iota, (size_t)n * sizeof(int));
+  int rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
+  if (rc == FSB_OK) {
+    iota_kernel<<<grid_for(n), 256, 0, st>>>(iota, n);
+    fsb_count_launch();
+    const int end_bit = bits_for(nkeys);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, keys_sorted, iota, d_perm, (long long)n, 0, end_bit, st);
+    e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_keys, keys_sorted, iota, d_perm, (long long)n, 0, end_bit, st);
+    fsb_count_launch(4);
+    if (e == cudaSuccess) {
+      row_ptr_from_sorted_kernel<<<grid_for(n + 1), 256, 0, st>>>(keys_sorted, n, nkeys, d_ptr);
+      fsb_count_launch();
+      e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "stable_perm_by_key", __FILE__, __LINE__);
+  }
+  cudaFree(keys_sorted); cudaFree(iota); cudaFree(tmp);
+  return rc;
+}
+
+namespace {
+// class key of a blocked-COO entry: block * kBlockedClasses + (local row mod kBlockedClasses)
+__global__ void blocked_keys_kernel(const int* __restrict__ rows, const long* __restrict__ blk_off, const int* __restrict__ start_row,
+                                    int nblocks, long long nnz, int* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    int lo = 0, hi = nblocks;  // largest b with blk_off[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (blk_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    keys[i] = lo * FSB_BLOCKED_CLASSES + ((rows[i] - start_row[lo]) & (FSB_BLOCKED_CLASSES - 1));
+  }
+}
+}  // namespace
+
+// Re-lay a freshly uploaded blocked COO into row-class buckets (see kernels_blocked.cu):
+// within each block, entries are stably bucketed by (local row mod 256), so a team of
+// lanes that owns a row class streams its own list in the stored (e.g. Hilbert) order.
+int fsb_blocked_relayout(fsb_matrix* A, cudaStream_t st) {
+  const long nnz = A->nnz;
+  const long nkeys_l = (long)A->nblocks * FSB_BLOCKED_CLASSES;
+  if (nkeys_l >= (1L << 31)) return fsb_set_error(FSB_EINVAL, "blocked: too many row blocks (%d)", A->nblocks);
+  const int nkeys = (int)nkeys_l;
+  FSB_CUDA(cudaMalloc(&A->row_ptr, ((size_t)nkeys + 1) * sizeof(int)));
+  A->bytes += ((size_t)nkeys + 1) * sizeof(int);
+  if (nnz == 0) {
+    FSB_CUDA(cudaMemsetAsync(A->row_ptr, 0, ((size_t)nkeys + 1) * sizeof(int), st));
+    return FSB_OK;
+  }
+  int *keys = nullptr, *perm = nullptr, *r2 = nullptr, *c2 = nullptr;
+  double* v2 = nullptr;
+  int rc = FSB_OK;
+  cudaError_t e = cudaMalloc(&keys, (size_t)nnz * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&perm, (size_t)nnz * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&r2, (size_t)nnz * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&c2, (size_t)nnz * 4);
+  if (e == cudaSuccess && A->has_vals) e = cudaMalloc(&v2, (size_t)nnz * 8);
+  if (e != cudaSuccess) rc = fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
+  if (rc == FSB_OK) {
+    blocked_keys_kernel<<<grid_for(nnz), 256, 0, st>>>(A->b_rows, A->blk_off, A->start_row, A->nblocks, nnz, keys);
+    fsb_count_launch();
+    rc = fsb_stable_perm_by_key(keys, nkeys, nnz, perm, A->row_ptr, st);
+  }
+  if (rc == FSB_OK) {
+    gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(r2, A->b_rows, perm, nnz);
+    gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(c2, A->b_cols, perm, nnz);
+    if (A->has_vals) gather_f64_kernel<<<grid_for(nnz), 256, 0, st>>>(v2, A->b_vals, perm, nnz);
+    fsb_count_launch(A->has_vals ? 3 : 2);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "blocked relayout", __FILE__, __LINE__);
+  }
+  if (rc == FSB_OK) {
+    cudaFree(A->b_rows); cudaFree(A->b_cols); cudaFree(A->b_vals);
+    A->b_rows = r2; A->b_cols = c2; A->b_vals = v2;
+    r2 = c2 = nullptr; v2 = nullptr;
+  }
+  cudaFree(keys); cudaFree(perm); cudaFree(r2); cudaFree(c2); cudaFree(v2);
+  return rc;
+}
+
+int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
+                               const int* d_cols, const double* d_vals, cudaStream_t st) {
+  return coo_to_csr_dev(out, nrow, ncol, nnz, d_rows, d_cols, d_vals, st);
+}
+
+int fsb_build_transpose(fsb_matrix* A, cudaStream_t st) {
+  if (A->T) return FSB_OK;
+  if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "transpose: CSR handles only");
+  int* rowid = nullptr;
+  const size_t n1 = (size_t)std::max<long>(A->nnz, 1);
+  FSB_CUDA(cudaMalloc(&rowid, n1 * sizeof(int)));
+  if (A->nnz > 0) {
+    expand_rows_kernel<<<grid_for(A->nnz), 256, 0, st>>>(A->row_ptr, A->nrow, A->nnz, rowid);
+    fsb_count_launch();
+  }
+  fsb_matrix* T = new fsb_matrix();
+  int rc = coo_to_csr_dev(T, A->ncol, A->nrow, A->nnz, A->cols, rowid, A->vals, st);
+  cudaFree(rowid);
+  if (rc != FSB_OK) {
+    cudaFree(T->row_ptr); cudaFree(T->cols); cudaFree(T->vals);
+    delete T;
+    return rc;
+  }
+  A->T = T;
+  return FSB_OK;
+}
+
+extern "C" int fsb_synth_coo_dev(unsigned long long seed, int dist, long nnz, int nrow, int ncol,
+                                 int* d_rows, int* d_cols, double* d_vals, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (nnz < 0 || nrow <= 0 || ncol <= 0 || !d_rows || !d_cols) return fsb_set_error(FSB_EINVAL, "synth: bad arguments");
+  if (nnz == 0) return FSB_OK;
+  synth_kernel<<<grid_for(nnz), 256, 0, fsb_pick_stream(stream)>>>(seed, dist, nnz, nrow, ncol, d_rows, d_cols, d_vals);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+extern "C" int fsb_synth_coo_host(unsigned long long seed, int dist, long nnz, int nrow, int ncol,
+                                  int* rows, int* cols, double* vals) {
+  if (nnz < 0 || nrow <= 0 || ncol <= 0 || !rows || !cols) return fsb_set_error(FSB_EINVAL, "synth: bad arguments");
+  for (long j = 0; j < nnz; ++j) {
+    rows[j] = fsb_synth_row(seed, (unsigned long long)j, nrow);
+    cols[j] = fsb_synth_col(seed, (unsigned long long)j, ncol, dist);
+    if (vals) vals[j] = fsb_synth_val(seed, (unsigned long long)j);
+  }
+  return FSB_OK;
+}

@@ -1,0 +1,282 @@
+// kernels_csr.cu -- CSR sparse x dense products on sm_100a.
+//
+// Replaces the OpenMP row loops of the reference:
+//   bcsr_A_mul_B csr.h:149-161, _B2/_B4/_B8/_B8_auto csr.h:164-254,
+//   bcsr_A_mul_Bn csr.h:257-280, bcsr_A_mul_B32n csr.h:283-302,
+//   csr_A_mul_B csr.h:425-438, csr_A_mul_Bn csr.h:441-465,
+//   bcsr_AA_mul_B / parallel_bcsr_AA_mul_B csr.h:305-355 (fused mode).
+//
+// Design (not a port: the reference gives each CPU thread whole rows and a private
+// accumulator vector).  Here a TEAM of TW lanes owns one row.  The team streams the
+// row's column indices with one coalesced load per TW entries, then hands each index
+// to a SUB-GROUP of G lanes by warp shuffle; the G lanes gather G*VEC consecutive
+// doubles of the dense operand row in ONE vector LDG per lane (VEC = 4 -> a single
+// 256-bit LDG.E.256; at R = 32 eight lanes fetch a whole 256-byte X row and a warp
+// has four X rows in flight per instruction).  TW/G sub-groups work on different
+// nonzeros of the same row, so partial sums are combined by shuffle-xor at the end
+// and sub-group 0 writes the Y row with a streaming store.  No atomics, no shared
+// memory, deterministic.  HBM-bound: no tensor cores (arithmetic intensity
+// <= 0.125 flop/B).
+//
+// Index arithmetic is 64-bit wherever a row index is multiplied by R (the host
+// structs are int32; see SURVEY "32-bit indexing limits").
+#include <algorithm>
+
+#include "fsb_device.cuh"
+#include "fsb_internal.h"
+
+using namespace fsbdev;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int TW, int G, int VEC, bool VALS>
+__global__ void __launch_bounds__(kThreads)
+csr_spmm_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                const double* __restrict__ vals, const double* __restrict__ X,
+                double* __restrict__ Y, int R, int col0, int ncols) {
+  constexpr int NSUB = TW / G;            // sub-groups (nonzeros in flight) per team
+  constexpr int U = (G >= 4) ? 4 : G;     // gathers in flight per lane
+  const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(gt / TW);
+  if (row >= nrow) return;                // whole team leaves together
+  const int lane = threadIdx.x & 31;
+  const int tl = lane & (TW - 1);
+  const int sub = tl / G;
+  const int l = tl & (G - 1);
+  const unsigned tmask = (TW == 32) ? 0xffffffffu : (((1u << TW) - 1u) << (lane - tl));
+  const bool col_ok = l * VEC < ncols;
+  const double* xbase = X + col0 + l * VEC;
+
+  const int start = __ldg(row_ptr + row);
+  const int end = __ldg(row_ptr + row + 1);
+  double acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+
+  for (int base = start; base < end; base += TW) {
+    const int idx = base + tl;
+    int myc = 0;
+    double myv = 0.0;
+    if (idx < end) {
+      myc = ld_stream_s32(cols + idx);
+      if (VALS) myv = ld_stream_f64(vals + idx);
+    }
+    const int n_here = min(TW, end - base);
+    for (int s0 = 0; s0 < n_here; s0 += NSUB * U) {
+      double xr[U][VEC];
+      double vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = s0 + u * NSUB + sub;
+        const int c = __shfl_sync(tmask, myc, j & (TW - 1), TW);
+        if (VALS) vv[u] = shfl_f64(tmask, myv, j & (TW - 1), TW);
+        if (j < n_here && col_ok) {
+          XLoad<VEC>::ld(xr[u], xbase + (long long)c * R);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) xr[u][v] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          acc[v] = VALS ? fma(xr[u][v], vv[u], acc[v]) : acc[v] + xr[u][v];
+    }
+  }
+#pragma unroll
+  for (int off = G; off < TW; off <<= 1)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] += shfl_xor_f64(tmask, acc[v], off, TW);
+  if (sub == 0 && col_ok) YStore<VEC>::st(Y + (long long)row * R + col0 + l * VEC, acc);
+}
+
+// Fused y = A'(A x) (+ the caller pre-loads Y with lambda*X): per row, gather-sum
+// xv = sum X[c,:], then scatter xv to Y[c,:] with fp64 red.global.add at L2.
+// Order of the scatter adds is not deterministic; results agree with the two-pass
+// mode to ~1e-15 relative per add (SURVEY "Determinism vs tolerance").
+template <int TW, int G, bool VALS>
+__global__ void __launch_bounds__(kThreads)
+csr_ata_fused_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                     const double* __restrict__ vals, const double* __restrict__ X,
+                     double* __restrict__ Y, int R) {
+  constexpr int NSUB = TW / G;
+  const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const int row = (int)(gt / TW);
+  if (row >= nrow) return;
+  const int lane = threadIdx.x & 31;
+  const int tl = lane & (TW - 1);
+  const int sub = tl / G;
+  const int l = tl & (G - 1);
+  const unsigned tmask = (TW == 32) ? 0xffffffffu : (((1u << TW) - 1u) << (lane - tl));
+  const bool col_ok = l < R;
+  const int start = __ldg(row_ptr + row);
+  const int end = __ldg(row_ptr + row + 1);
+  double acc = 0.0;
+  for (int base = start; base < end; base += TW) {
+    const int idx = base + tl;
+    int myc = 0;
+    double myv = 0.0;
+    if (idx < end) {
+      myc = __ldg(cols + idx);          // re-read by the scatter phase: let L1 keep it
+      if (VALS) myv = __ldg(vals + idx);
+    }
+    const int n_here = min(TW, end - base);
+    for (int s0 = 0; s0 < n_here; s0 += NSUB) {
+      const int j = s0 + sub;
+      const int c = __shfl_sync(tmask, myc, j & (TW - 1), TW);
+      const double v = VALS ? shfl_f64(tmask, myv, j & (TW - 1), TW) : 1.0;
+      if (j < n_here && col_ok) acc = fma(__ldg(X + (long long)c * R + l), v, acc);
+    }
+  }
+#pragma unroll
+  for (int off = G; off < TW; off <<= 1) acc += shfl_xor_f64(tmask, acc, off, TW);
+  for (int base = start; base < end; base += TW) {
+    const int idx = base + tl;
+    int myc = 0;
+    double myv = 0.0;
+    if (idx < end) {
+      myc = __ldg(cols + idx);
+      if (VALS) myv = __ldg(vals + idx);
+    }
+    const int n_here = min(TW, end - base);
+    for (int s0 = 0; s0 < n_here; s0 += NSUB) {
+      const int j = s0 + sub;
+      const int c = __shfl_sync(tmask, myc, j & (TW - 1), TW);
+      const double v = VALS ? shfl_f64(tmask, myv, j & (TW - 1), TW) : 1.0;
+      if (j < n_here && col_ok) red_add_f64(Y + (long long)c * R + l, acc * v);
+    }
+  }
+}
+
+__global__ void scale_copy_kernel(double* __restrict__ Y, const double* __restrict__ X, double lambda, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) Y[i] = lambda * X[i];
+}
+
+int g_tw = 0, g_g = 0, g_vec = 0, g_slabs = 0;
+
+inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+inline int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p <<= 1; return p; }
+
+template <int TW, int G, int VEC, bool VALS>
+void launch_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, cudaStream_t st) {
+  const long long threads = (long long)A->nrow * TW;
+  const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+  csr_spmm_kernel<TW, G, VEC, VALS><<<grid, kThreads, 0, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols);
+}
+
+template <int TW, int G, bool VALS>
+void launch_fused(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+  const long long threads = (long long)A->nrow * TW;
+  const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+  csr_ata_fused_kernel<TW, G, VALS><<<grid, kThreads, 0, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R);
+}
+
+template <int TW, int G, int VEC>
+bool dispatch_vals(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, cudaStream_t st) {
+  if (A->has_vals) launch_spmm<TW, G, VEC, true>(A, dY, dX, R, col0, ncols, st);
+  else launch_spmm<TW, G, VEC, false>(A, dY, dX, R, col0, ncols, st);
+  return true;
+}
+
+template <int TW, int G>
+bool dispatch_vec(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, cudaStream_t st) {
+  switch (vec) {
+    case 1: return dispatch_vals<TW, G, 1>(A, dY, dX, R, col0, ncols, st);
+    case 2: return dispatch_vals<TW, G, 2>(A, dY, dX, R, col0, ncols, st);
+    case 4: return dispatch_vals<TW, G, 4>(A, dY, dX, R, col0, ncols, st);
+  }
+  return false;
+}
+
+#define FSB_TWG_TABLE(X) \
+  X(1, 1) X(2, 1) X(4, 1) X(8, 1) X(16, 1) X(32, 1) \
+  X(2, 2) X(4, 2) X(8, 2) X(16, 2) X(32, 2)         \
+  X(4, 4) X(8, 4) X(16, 4) X(32, 4)                 \
+  X(8, 8) X(16, 8) X(32, 8)                         \
+  X(16, 16) X(32, 16)                               \
+  X(32, 32)
+
+bool dispatch_spmm(int tw, int g, int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, cudaStream_t st) {
+#define X(TW_, G_) if (tw == TW_ && g == G_) return dispatch_vec<TW_, G_>(vec, A, dY, dX, R, col0, ncols, st);
+  FSB_TWG_TABLE(X)
+#undef X
+  return false;
+}
+
+bool dispatch_fused(int tw, int g, const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+#define X(TW_, G_)                                                      \
+  if (tw == TW_ && g == G_) {                                           \
+    if (A->has_vals) launch_fused<TW_, G_, true>(A, dY, dX, R, st);     \
+    else launch_fused<TW_, G_, false>(A, dY, dX, R, st);                \
+    return true;                                                        \
+  }
+  FSB_TWG_TABLE(X)
+#undef X
+  return false;
+}
+
+// team width from the mean row length: enough sub-groups to cover a row in a couple
+// of steps without leaving most of them idle
+int pick_tw(int g, double avg_nnz) {
+  int want = pow2_floor(std::max(1, (int)(avg_nnz / 2.0)));
+  int ns = std::min(want, 32 / g);
+  return g * std::max(ns, 1);
+}
+
+}  // namespace
+
+void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs) {
+  g_tw = tw; g_g = g; g_vec = vec; g_slabs = slabs;
+}
+
+extern "C" int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs) {
+  auto pow2 = [](int x) { return x == 0 || (x > 0 && x <= 32 && (x & (x - 1)) == 0); };
+  if (!pow2(tw) || !pow2(g) || !(vec == 0 || vec == 1 || vec == 2 || vec == 4) || slabs < 0)
+    return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_spmm: tw, g must be 0 or a power of two <= 32; vec 0/1/2/4");
+  fsb_csr_spmm_set_tuning(tw, g, vec, slabs);
+  return FSB_OK;
+}
+
+int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+  if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
+  if (A->nrow == 0) return FSB_OK;
+  const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY;
+  int vec = (R % 4 == 0 && al % 32 == 0) ? 4 : (R % 2 == 0 && al % 16 == 0) ? 2 : 1;
+  if (g_vec && (R % g_vec == 0) && (al % (8 * g_vec) == 0)) vec = g_vec;
+  // columns handled per pass: at most 32 lanes * vec; optional slab split keeps the
+  // per-pass footprint of the dense operand inside L2
+  int per_pass = std::min(R, 32 * vec);
+  if (g_slabs > 1 && R % (g_slabs * vec) == 0) per_pass = std::min(per_pass, R / g_slabs);
+  int g = pow2_ceil((per_pass + vec - 1) / vec);
+  if (g_g && g_g >= g && g_g <= 32) g = g_g;
+  int tw = pick_tw(g, A->avg_row_nnz);
+  if (g_tw && g_tw >= g && g_tw <= 32) tw = g_tw;
+  for (int col0 = 0; col0 < R; col0 += per_pass) {
+    const int ncols = std::min(per_pass, R - col0);
+    if (!dispatch_spmm(tw, g, vec, A, dY, dX, R, col0, ncols, st))
+      return fsb_set_error(FSB_EINVAL, "spmm: no kernel for TW=%d G=%d VEC=%d", tw, g, vec);
+    FSB_KERNEL_CHECK();
+  }
+  return FSB_OK;
+}
+
+int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st) {
+  if (R <= 0 || R > 32) return fsb_set_error(FSB_EINVAL, "fused A'A: R must be 1..32 (got %d)", R);
+  const long long n = (long long)A->ncol * R;
+  if (n > 0) {
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    scale_copy_kernel<<<blocks, 256, 0, st>>>(dY, dX, lambda, n);
+    FSB_KERNEL_CHECK();
+  }
+  if (A->nrow == 0) return FSB_OK;
+  const int g = pow2_ceil(R);
+  const int tw = pick_tw(g, A->avg_row_nnz);
+  if (!dispatch_fused(tw, g, A, dY, dX, R, st)) return fsb_set_error(FSB_EINVAL, "fused A'A: no kernel for TW=%d G=%d", tw, g);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}

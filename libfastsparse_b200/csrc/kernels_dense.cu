@@ -1,0 +1,294 @@
+// kernels_dense.cu -- dense building blocks of the block conjugate-gradient solver.
+//
+// Replaces the OpenMP reductions and vector loops of the reference:
+//   pnormsq/pnormsq2/pouter2/pdot/pdot2sym linalg.h:15-73  -> gram_partial/gram_final
+//   solve2sym linalg.h:77-88                               -> small_solve_kernel (R x R)
+//   update loops cg.h:60-63,70-73,148-154,165-170,176-179  -> cg_* kernels below
+// All operands are tall-skinny row-major [n][R], R <= 32: streaming, HBM-bound passes.
+// Reductions are two-stage with a fixed order, so every rank of a multi-GPU solve
+// gets bit-identical Gram matrices and takes the same branches.
+#include <algorithm>
+
+#include "fsb_dense.h"
+#include "fsb_internal.h"
+
+namespace {
+
+constexpr int kGramCtas = 148 * 2;
+constexpr int kTile = 32;  // rows staged per step
+
+// partial[cta][Ra*Rb] = sum over this CTA's rows of Xa[i][a] * Xb[i][b]
+__global__ void __launch_bounds__(256)
+gram_partial_kernel(double* __restrict__ partial, const double* __restrict__ Xa, const double* __restrict__ Xb,
+                    long long n, int R) {
+  __shared__ double sa[kTile][33];
+  __shared__ double sb[kTile][33];
+  // thread owns entries e = tid + 256*q of the R x R result (q < 4)
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int tid = threadIdx.x;
+  const int RR = R * R;
+  for (long long base = (long long)blockIdx.x * kTile; base < n; base += (long long)gridDim.x * kTile) {
+    const int rows = (int)min((long long)kTile, n - base);
+    for (int e = tid; e < rows * R; e += 256) {
+      const int r = e / R, c = e - r * R;
+      sa[r][c] = Xa[(base + r) * R + c];
+      sb[r][c] = Xb[(base + r) * R + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + 256 * q;
+      if (e < RR) {
+        const int a = e / R, b = e - a * R;
+        double s = acc[q];
+        for (int r = 0; r < rows; ++r) s = fma(sa[r][a], sb[r][b], s);
+        acc[q] = s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = tid + 256 * q;
+    if (e < RR) partial[(size_t)blockIdx.x * RR + e] = acc[q];
+  }
+}
+
+__global__ void gram_final_kernel(double* __restrict__ G, const double* __restrict__ partial, int nparts, int RR) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= RR) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * RR + e];
+  G[e] = s;
+}
+
+__global__ void axpy_lambda_kernel(double* __restrict__ Y, const double* __restrict__ X, double lambda, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) Y[i] = fma(lambda, X[i], Y[i]);
+}
+
+// X = 0, Rm = P = B * diag(inorm)     (cg.h:44-48, 112-120)
+__global__ void cg_init_kernel(double* __restrict__ X, double* __restrict__ Rm, double* __restrict__ P,
+                               const double* __restrict__ B, const double* __restrict__ inorm, long long n, int R) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double r = B[i] * inorm[i % R];
+    X[i] = 0.0;
+    Rm[i] = r;
+    P[i] = r;
+  }
+}
+
+// norms from the Gram diagonal: norm[k] = sqrt(G[k][k]) (or 1 when !normalise)
+__global__ void cg_norms_kernel(double* __restrict__ norm, double* __restrict__ inorm, const double* __restrict__ G, int R, int normalise) {
+  const int k = threadIdx.x;
+  if (k >= R) return;
+  const double nv = normalise ? sqrt(G[k * R + k]) : 1.0;
+  norm[k] = nv;
+  inorm[k] = 1.0 / nv;
+}
+
+// Out1[i,:] += In1[i,:] * M ; Out2[i,:] -= In2[i,:] * M      (cg.h:148-154)
+// or (mode 1) Out1[i,:] = Add[i,:] + Out1[i,:] * M            (cg.h:165-170)
+// M is R x R, M[k][j] = coefficient of input column k in output column j.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+cg_rowmix_kernel(double* __restrict__ O1, const double* __restrict__ I1, double* __restrict__ O2,
+                 const double* __restrict__ I2, const double* __restrict__ M, long long n, int R) {
+  __shared__ double sm[32][33];
+  __shared__ double s1[8][33];
+  __shared__ double s2[8][33];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < R * R; e += 256) sm[e / R][e % R] = M[e];
+  const int r = tid >> 5, j = tid & 31;
+  for (long long base = (long long)blockIdx.x * 8; base < n; base += (long long)gridDim.x * 8) {
+    const long long row = base + r;
+    const bool ok = row < n && j < R;
+    __syncthreads();
+    if (ok) {
+      s1[r][j] = (MODE == 0) ? I1[row * R + j] : O1[row * R + j];
+      if (MODE == 0) s2[r][j] = I2[row * R + j];
+    }
+    __syncthreads();
+    if (ok) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < R; ++k) {
+        const double m = sm[k][j];
+        a = fma(s1[r][k], m, a);
+        if (MODE == 0) b = fma(s2[r][k], m, b);
+      }
+      if (MODE == 0) {
+        O1[row * R + j] += a;
+        O2[row * R + j] -= b;
+      } else {
+        O1[row * R + j] = I1[row * R + j] + a;
+      }
+    }
+  }
+}
+
+__global__ void cg_scale_cols_kernel(double* __restrict__ X, const double* __restrict__ norm, long long n, int R) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) X[i] *= norm[i % R];
+}
+
+// Solve A M = RHS for M (all R x R, row-major; A symmetric positive definite) by
+// Cholesky A = L L' in one CTA.  Generalises the closed-form 2x2 solve2sym
+// (linalg.h:77-88).  status[0] is set to 1 when a pivot is not safely positive.
+// Also (check != 0) evaluates the stopping rule of bsbm_cg2 (cg.h:158): status[1] = 1
+// when every diagonal entry of RHS is <= thr.
+__global__ void small_solve_kernel(double* __restrict__ M, const double* __restrict__ A, const double* __restrict__ RHS,
+                                   int R, int* __restrict__ status, int check, double thr) {
+  __shared__ double L[32][33];
+  __shared__ double Bm[32][33];
+  __shared__ int bad;
+  const int tid = threadIdx.x;  // 32 x 32 threads: (i, j)
+  const int i = tid >> 5, j = tid & 31;
+  if (tid == 0) bad = 0;
+  if (i < R && j < R) {
+    L[i][j] = A[i * R + j];
+    Bm[i][j] = RHS[i * R + j];
+  }
+  __syncthreads();
+  double amax = 0.0;
+  for (int d = 0; d < R; ++d) amax = fmax(amax, fabs(L[d][d]));
+  __syncthreads();
+  for (int k = 0; k < R; ++k) {
+    if (tid == 0) {
+      const double piv = L[k][k];
+      if (!(piv > 1e-14 * amax)) { bad = 1; L[k][k] = 1.0; } else L[k][k] = sqrt(piv);
+    }
+    __syncthreads();
+    if (j == k && i > k && i < R) L[i][k] /= L[k][k];
+    __syncthreads();
+    if (i > k && j > k && j <= i && i < R) L[i][j] -= L[i][k] * L[j][k];
+    __syncthreads();
+  }
+  // forward substitution L Z = B (column j handled by the threads with i == 0)
+  if (i == 0 && j < R) {
+    for (int r = 0; r < R; ++r) {
+      double s = Bm[r][j];
+      for (int c = 0; c < r; ++c) s -= L[r][c] * Bm[c][j];
+      Bm[r][j] = s / L[r][r];
+    }
+    for (int r = R - 1; r >= 0; --r) {
+      double s = Bm[r][j];
+      for (int c = r + 1; c < R; ++c) s -= L[c][r] * Bm[c][j];
+      Bm[r][j] = s / L[r][r];
+    }
+  }
+  __syncthreads();
+  if (i < R && j < R) M[i * R + j] = Bm[i][j];
+  if (tid == 0) {
+    status[0] = bad;
+    if (check) {
+      int done = 1;
+      for (int d = 0; d < R; ++d)
+        if (!(RHS[d * R + d] <= thr)) done = 0;
+      status[1] = done;
+    }
+  }
+}
+
+// status[1] = all diag(G) <= thr  (stopping rule alone)
+__global__ void diag_check_kernel(const double* __restrict__ G, int R, double thr, int* __restrict__ status) {
+  if (threadIdx.x == 0) {
+    int done = 1;
+    for (int d = 0; d < R; ++d)
+      if (!(G[d * R + d] <= thr)) done = 0;
+    status[1] = done;
+  }
+}
+
+inline int grid_for(long long n) { return (int)std::min<long long>((n + 255) / 256, 148LL * 16); }
+
+}  // namespace
+
+int fsb_dense_gram_into(double* dG, double* dPartial, const double* dXa, const double* dXb, long n, int R, cudaStream_t st) {
+  if (R < 1 || R > 32) return fsb_set_error(FSB_EINVAL, "gram: R must be 1..32 (got %d)", R);
+  const int ctas = (int)std::max<long long>(1, std::min<long long>(kGramCtas, (n + kTile - 1) / kTile));
+  gram_partial_kernel<<<ctas, 256, 0, st>>>(dPartial, dXa, dXb, n, R);
+  FSB_KERNEL_CHECK();
+  gram_final_kernel<<<(R * R + 255) / 256, 256, 0, st>>>(dG, dPartial, ctas, R * R);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+size_t fsb_dense_gram_scratch_bytes(int R) { return (size_t)kGramCtas * R * R * sizeof(double); }
+
+int fsb_dense_axpy_lambda(double* dY, const double* dX, double lambda, long n, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  axpy_lambda_kernel<<<grid_for(n), 256, 0, st>>>(dY, dX, lambda, n);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_cg_norms(double* dNorm, double* dInorm, const double* dG, int R, int normalise, cudaStream_t st) {
+  cg_norms_kernel<<<1, 32, 0, st>>>(dNorm, dInorm, dG, R, normalise);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_cg_init(double* dX, double* dRm, double* dP, const double* dB, const double* dInorm, long n, int R, cudaStream_t st) {
+  const long long tot = (long long)n * R;
+  if (tot <= 0) return FSB_OK;
+  cg_init_kernel<<<grid_for(tot), 256, 0, st>>>(dX, dRm, dP, dB, dInorm, tot, R);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_cg_update_xr(double* dX, const double* dP, double* dRm, const double* dKP, const double* dAlpha, long n, int R, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  const int ctas = (int)std::min<long long>((n + 7) / 8, 148LL * 8);
+  cg_rowmix_kernel<0><<<ctas, 256, 0, st>>>(dX, dP, dRm, dKP, dAlpha, n, R);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_cg_update_p(double* dP, const double* dRm, const double* dPsi, long n, int R, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  const int ctas = (int)std::min<long long>((n + 7) / 8, 148LL * 8);
+  cg_rowmix_kernel<1><<<ctas, 256, 0, st>>>(dP, dRm, nullptr, nullptr, dPsi, n, R);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_scale_cols(double* dX, const double* dNorm, long n, int R, cudaStream_t st) {
+  const long long tot = (long long)n * R;
+  if (tot <= 0) return FSB_OK;
+  cg_scale_cols_kernel<<<grid_for(tot), 256, 0, st>>>(dX, dNorm, tot, R);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_small_solve(double* dM, const double* dA, const double* dRHS, int R, int* dStatus, int check, double thr, cudaStream_t st) {
+  small_solve_kernel<<<1, 1024, 0, st>>>(dM, dA, dRHS, R, dStatus, check, thr);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+int fsb_dense_diag_check(const double* dG, int R, double thr, int* dStatus, cudaStream_t st) {
+  diag_check_kernel<<<1, 32, 0, st>>>(dG, R, thr, dStatus);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+extern "C" int fsb_gram_dev(double* G_host, const double* dXa, const double* dXb, long n, int R, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!G_host || !dXa || !dXb || n < 0) return fsb_set_error(FSB_EINVAL, "fsb_gram_dev: bad argument");
+  cudaStream_t st = fsb_pick_stream(stream);
+  double *dG = nullptr, *dPart = nullptr;
+  FSB_CUDA(cudaMalloc(&dG, (size_t)R * R * 8));
+  cudaError_t e = cudaMalloc(&dPart, fsb_dense_gram_scratch_bytes(R));
+  int rc = e == cudaSuccess ? fsb_dense_gram_into(dG, dPart, dXa, dXb, n, R, st) : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
+  if (rc == FSB_OK) {
+    e = cudaMemcpyAsync(G_host, dG, (size_t)R * R * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "gram readback", __FILE__, __LINE__);
+  }
+  cudaFree(dG); cudaFree(dPart);
+  return rc;
+}

@@ -1,0 +1,354 @@
+"""GPU parity tests (run with -m gpu on a B200): every product / solve goes through the
+C-ABI library and is compared with the CPU oracle (oracle/fsoracle.c, pinned against the
+reference by tests/test_oracle_golden.py) and with the golden outputs of the unmodified
+reference.  Index/structure results must be bit-exact; fp64 products must agree to
+1e-12 * max(1, sum|terms|) (summation order differs)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import libfastsparse_b200 as fs
+import oracle
+from conftest import DATA, assert_close, golden, rhs_matrix, test_vec as tvec
+from oracle import O, dp, f64, i32, ip
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    assert fs.device_count() >= 1
+    before = fs.launch_count()
+    yield
+    assert fs.launch_count() > before, "no kernel of libfastsparse_b200.so was launched"
+
+
+def row_scale(nrow, rows, xmax=2.0, vmax=1.0):
+    return xmax * vmax * max(1, int(np.bincount(rows, minlength=nrow).max()) if rows.size else 1)
+
+
+# ------------------------------------------------------------------ reference known answers
+def test_known_answers_tiny():     # test_sparse.c:30-44, 114-135, 159-173, 412-468
+    A = fs.new_sbm(4, 3, 5, [0, 3, 3, 1, 2], [0, 2, 0, 2, 1])
+    x = np.array([0.5, -0.7, 1.9]); y = np.zeros(4)
+    fs.A_mul_B(y, A, x); assert list(y) == [0.5, 1.9, -0.7, 2.4]
+    Cb = fs.cbcsr_from_sbm(A, 2); y[:] = 0
+    fs.cbcsr_A_mul_B(y, Cb, x); assert list(y) == [0.5, 1.9, -0.7, 2.4]
+    z = np.zeros(3); fs.At_mul_B(z, A, np.array([0.2, 1.3, -0.7, -0.5])); assert np.max(np.abs(z - [-0.3, -0.7, 0.8])) < 1e-15
+    D = fs.new_sdm(6, 4, 11, [1, 1, 3, 4, 1, 4, 5, 0, 1, 2, 4], [0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3],
+                   [0.65, 0.84, 0.54, 0.59, 0.51, 0.27, 0.23, 0.94, 0.66, 0.31, 0.92])
+    yt = np.array([2.162, 2.224, 0.713, -0.378, 2.216, 0.437]); y6 = np.zeros(6)
+    fs.sdm_A_mul_B(y6, D, np.array([0.5, -0.7, 1.9, 2.3])); assert np.max(np.abs(y6 - yt)) < 1e-6
+    M = fs.new_csr(D.nnz, 6, 4, D.rows, D.cols, D.vals)
+    fs.csr_A_mul_B(y6, M, np.array([0.5, -0.7, 1.9, 2.3])); assert np.max(np.abs(y6 - yt)) < 1e-6
+    Y = np.zeros(12); fs.csr_A_mul_Bn(Y, M, np.array([0.5, 5.0, -0.7, -7.0, 1.9, 19.0, 2.3, 23.0]), 2)
+    assert np.max(np.abs(Y.reshape(6, 2) - np.stack([yt, 10 * yt], 1))) < 1e-6
+    z4 = np.zeros(4); fs.sdm_At_mul_B(z4, D, np.array([0.59, 0.37, 0.14, 0.21, 0.40, 0.81]))
+    assert np.max(np.abs(z4 - [0.2405, 0.6602, 0.483, 1.2102])) < 1e-6
+
+
+def test_known_answers_fixture():  # test_sparse.c:46-112, 137-157
+    A = fs.read_sbm(os.path.join(DATA, "sbm-100-50.data"))
+    B = fs.bcsr_from_sbm(A)
+    x = tvec(A.ncol); y = np.zeros(A.nrow); y2 = np.zeros(A.nrow)
+    fs.A_mul_B(y2, A, x); fs.bcsr_A_mul_B(y, B, x)
+    assert abs(y[0] - 1.70095) < 1e-4 and abs(y[99] + 0.174905) < 1e-4 and np.max(np.abs(y - y2)) < 1e-12
+    assert abs(y[0] - 1.7009531873605335) < 1e-13 and abs(y.sum() - 42.631240828393558) < 1e-11
+    tmp = np.zeros(A.nrow); z2 = np.zeros(A.ncol); z = np.zeros(A.ncol)
+    fs.A_mul_B(tmp, A, x); fs.At_mul_B(z2, A, tmp)
+    fs.bcsr_AA_mul_B(z, B, x); assert np.max(np.abs(z - z2)) < 1e-10
+    assert abs(z[0] - 28.810541791856551) < 1e-11 and abs(z[49] - 16.518731587972916) < 1e-11
+    fs.parallel_bcsr_AA_mul_B(z, B, x, None); assert np.max(np.abs(z - z2)) < 1e-10
+    Cb = fs.cbcsr_from_sbm(A, 8); fs.cbcsr_A_mul_B(y, Cb, x); assert np.max(np.abs(y - y2)) < 1e-12
+
+
+# ------------------------------------------------------------------ golden fixtures of the unmodified reference
+@pytest.mark.parametrize("name", ["sbm_100_50", "rand_bin_300_70"])
+def test_binary_products_vs_reference_golden(name):
+    g = golden(name)
+    nrow, ncol, rows, cols = int(g["nrow"]), int(g["ncol"]), g["rows"], g["cols"]
+    x, xt = g["x"], g["xt"]
+    sc = row_scale(nrow, rows); sct = row_scale(ncol, cols)
+    A = fs.new_sbm(nrow, ncol, rows.size, rows.copy(), cols.copy())
+    y = np.zeros(nrow); fs.A_mul_B(y, A, x); assert_close(y, g["coo_Ax"], sc, what="A_mul_B")
+    z = np.zeros(ncol); fs.At_mul_B(z, A, xt); assert_close(z, g["coo_Atx"], sct, what="At_mul_B")
+    B = fs.bcsr_from_sbm(A)
+    fs.bcsr_A_mul_B(y, B, x); assert_close(y, g["csr_Ax"], sc, what="bcsr_A_mul_B")
+    for R in map(int, g["Rs"]):
+        Y = np.zeros(nrow * R); fs.bcsr_A_mul_Bn(Y, B, g[f"X{R}"], R); assert_close(Y, g[f"csr_AX{R}_Bn"], sc, what=f"bcsr_A_mul_Bn R={R}")
+        if R <= 32:
+            Y[:] = 0; fs.bcsr_A_mul_B32n(Y, B, g[f"X{R}"], R); assert_close(Y, g[f"csr_AX{R}_B32n"], sc, what=f"B32n R={R}")
+        fixed = {2: fs.bcsr_A_mul_B2, 4: fs.bcsr_A_mul_B4, 8: fs.bcsr_A_mul_B8}.get(R)
+        if fixed:
+            Y[:] = 0; fixed(Y, B, g[f"X{R}"]); assert_close(Y, g[f"csr_AX{R}_fixed"], sc, what=f"fixed R={R}")
+        if R == 8:
+            Y[:] = 0; fs.bcsr_A_mul_B8_auto(Y, B, g["X8"]); assert_close(Y, g["csr_AX8_auto"], sc, what="B8_auto")
+        # transposed CSR product (new entry point): oracle = At_mul_B column by column
+        Xt = rhs_matrix(nrow, R); Z = np.zeros(ncol * R); fs.bcsr_At_mul_Bn(Z, B, Xt, R)
+        want = np.stack([oracle.coo_mul(nrow, rows, cols, None, Xt[:, k], transpose=True, ncol=ncol) for k in range(R)], 1)
+        assert_close(Z, want, sct, what=f"bcsr_At_mul_Bn R={R}")
+    for mode in (0, 1):
+        fs.bcsr_AA_mul_B(z, B, x, mode=mode); assert_close(z, g["csr_AAx"], sc * sct, what=f"AA mode {mode}")
+    Cb = fs.cbcsr_from_sbm(A, int(g["colblock"]))
+    fs.cbcsr_A_mul_B(y, Cb, x); assert_close(y, g["cb_Ax"], sc, what="cbcsr_A_mul_B")
+    for R in map(int, g["Rs"]):
+        Y = np.zeros(nrow * R); fs.cbcsr_A_mul_Bn(Y, Cb, g[f"X{R}"], R); assert_close(Y, g[f"csr_AX{R}_Bn"], sc, what=f"cbcsr_A_mul_Bn R={R}")
+    bs = int(g["bs"])
+    for sorter in (None, fs.sort_bsbm, fs.sort_bsbm_byrow):
+        Bl = fs.new_bsbm(A, bs)
+        if sorter:
+            sorter(Bl)
+        fs.bsbm_A_mul_B(y, Bl, x); assert_close(y, g["blkh_Ax"], sc, what="bsbm_A_mul_B")
+        for R in map(int, g["Rs"]):
+            Y = np.zeros(nrow * R); fs.bsbm_A_mul_Bn(Y, Bl, g[f"X{R}"], R); assert_close(Y, g[f"blkh_AX{R}_Bn"], sc, what=f"bsbm_A_mul_Bn R={R}")
+        Y = np.zeros(nrow * 2); fs.bsbm_A_mul_B2(Y, Bl, g["X2"]); assert_close(Y, g["blkh_AX2_fixed"], sc, what="bsbm_B2")
+        Y = np.zeros(nrow * 4); fs.bsbm_A_mul_B4(Y, Bl, g["X4"]); assert_close(Y, g["blkh_AX4_fixed"], sc, what="bsbm_B4")
+
+
+@pytest.mark.parametrize("name", ["sdm_100_50", "rand_dbl_257_129"])
+def test_double_products_vs_reference_golden(name):
+    g = golden(name)
+    nrow, ncol, rows, cols, vals = int(g["nrow"]), int(g["ncol"]), g["rows"], g["cols"], g["vals"]
+    x, xt = g["x"], g["xt"]
+    sc = row_scale(nrow, rows); sct = row_scale(ncol, cols)
+    A = fs.new_sdm(nrow, ncol, rows.size, rows.copy(), cols.copy(), vals.copy())
+    y = np.zeros(nrow); fs.sdm_A_mul_B(y, A, x); assert_close(y, g["coo_Ax"], sc, what="sdm_A_mul_B")
+    z = np.zeros(ncol); fs.sdm_At_mul_B(z, A, xt); assert_close(z, g["coo_Atx"], sct, what="sdm_At_mul_B")
+    M = fs.new_csr(A.nnz, nrow, ncol, A.rows, A.cols, A.vals)
+    fs.csr_A_mul_B(y, M, x); assert_close(y, g["csr_Ax"], sc, what="csr_A_mul_B")
+    for R in map(int, g["Rs"]):
+        Y = np.zeros(nrow * R); fs.csr_A_mul_Bn(Y, M, g[f"X{R}"], R); assert_close(Y, g[f"csr_AX{R}_Bn"], sc, what=f"csr_A_mul_Bn R={R}")
+    Bl = fs.new_bsdm(A, int(g["bs"]))
+    fs.bsdm_A_mul_B(y, Bl, x); assert_close(y, g["blkh_Ax"], sc, what="bsdm_A_mul_B unsorted")
+    fs.sort_bsdm(Bl)
+    fs.bsdm_A_mul_B(y, Bl, x); assert_close(y, g["blkh_Ax"], sc, what="bsdm_A_mul_B sorted")
+
+
+# ------------------------------------------------------------------ ragged / edge cases against the oracle
+def _random_case(rng, nrow, ncol, nnz, long_row=0):
+    rows = rng.integers(0, nrow, nnz, dtype=np.int32); cols = rng.integers(0, ncol, nnz, dtype=np.int32)
+    if long_row:
+        rows[:long_row] = nrow // 2          # one very long row (and, transposed, one very hot column)
+    dead = rng.integers(0, nrow, max(1, nrow // 5))
+    rows[np.isin(rows, dead)] = (dead[0] + 1) % nrow     # empty rows
+    return rows, cols, rng.random(nnz)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 8, 16, 17, 31, 32, 33, 64, 100])
+def test_csr_products_ragged(R):
+    rng = np.random.default_rng(R)
+    nrow, ncol, nnz = 3001, 777, 40000
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=5000)
+    X = f64(rng.standard_normal((ncol, R)))
+    for v in (None, vals):
+        rp, cc, vv = oracle.csr_from_coo(nrow, rows, cols, v)
+        M = fs.BinaryCSR(nrow, ncol, rp, cc, vv)
+        Y = np.zeros(nrow * R); fs.bcsr_A_mul_Bn(Y, M, X, R)
+        sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(X), R)).reshape(-1)
+        assert_close(Y, oracle.csr_mul(nrow, rp, cc, vv, X, R), sc, what=f"csr R={R} vals={v is not None}")
+        Xt = f64(rng.standard_normal((nrow, R))); Z = np.zeros(ncol * R); fs.bcsr_At_mul_Bn(Z, M, Xt, R)
+        trp, tcc, tvv = oracle.csr_from_coo(ncol, cols, rows, v)
+        sct = np.abs(oracle.csr_mul(ncol, trp, tcc, np.abs(tvv) if tvv is not None else None, np.abs(Xt), R)).reshape(-1)
+        assert_close(Z, oracle.csr_mul(ncol, trp, tcc, tvv, Xt, R), sct, what=f"csr^T R={R} vals={v is not None}")
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 8, 32, 40])
+@pytest.mark.parametrize("bs", [1, 7, 64, 500, 5000])
+def test_blocked_products_ragged(R, bs):
+    rng = np.random.default_rng(R * 1000 + bs)
+    nrow, ncol, nnz = 2000, 333, 15000
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=600)
+    X = f64(rng.standard_normal((ncol, R)))
+    for v in (None, vals):
+        A = fs.SparseBinaryMatrix(nrow, ncol, rows, cols) if v is None else fs.SparseDoubleMatrix(nrow, ncol, rows, cols, v)
+        Bl = fs.new_bsbm(A, bs); fs.sort_bsbm(Bl)
+        Bo = oracle.blocked_from_coo(nrow, ncol, bs, rows, cols, v); O.fso_sort_blocked_hilbert(Bo.ref())
+        want = oracle.blocked_mul(Bo, X, R)
+        Y = np.zeros(nrow * R); fs.bsbm_A_mul_Bn(Y, Bl, X, R)
+        rp, cc, vv = oracle.csr_from_coo(nrow, rows, cols, v)
+        sc = np.abs(oracle.csr_mul(nrow, rp, cc, vv, np.abs(X), R)).reshape(-1)
+        assert_close(Y, want, sc, what=f"blocked R={R} bs={bs} vals={v is not None}")
+
+
+@pytest.mark.parametrize("R", [1, 4, 32])
+@pytest.mark.parametrize("colblock", [1, 5, 64, 1000])
+def test_cbcsr_products_ragged(R, colblock):
+    rng = np.random.default_rng(R * 7 + colblock)
+    nrow, ncol, nnz = 1500, 640, 20000
+    rows, cols, _ = _random_case(rng, nrow, ncol, nnz, long_row=3000)
+    X = f64(rng.standard_normal((ncol, R)))
+    Cb = fs.new_cbcsr(colblock, nnz, nrow, ncol, rows, cols)
+    Y = np.zeros(nrow * R); fs.cbcsr_A_mul_Bn(Y, Cb, X, R)
+    rp, cc, _ = oracle.csr_from_coo(nrow, rows, cols)
+    sc = np.abs(oracle.csr_mul(nrow, rp, cc, None, np.abs(X), R)).reshape(-1)
+    assert_close(Y, oracle.csr_mul(nrow, rp, cc, None, X, R), sc, what=f"cbcsr R={R} colblock={colblock}")
+    if R == 1:   # exact block-major association of the reference
+        nb, crp, ccc = oracle.cbcsr_from_coo(nrow, ncol, colblock, rows, cols)
+        y = np.zeros(nrow); O.fso_cbcsr_A_mul_B(dp(y), nrow, nb, ip(crp), ip(ccc), dp(f64(X[:, 0])))
+        assert_close(Y, y, sc, what="cbcsr vs fso_cbcsr_A_mul_B")
+
+
+def test_empty_and_degenerate_shapes():
+    for nrow, ncol in [(1, 1), (5, 3), (64, 1)]:
+        rp = np.zeros(nrow + 1, np.int32)
+        M = fs.BinaryCSR(nrow, ncol, rp, np.zeros(0, np.int32))
+        Y = np.full(nrow * 3, 7.0); fs.bcsr_A_mul_Bn(Y, M, np.ones(ncol * 3), 3)
+        assert not Y.any()                                           # outputs are fully overwritten
+        Z = np.full(ncol * 3, 7.0); fs.bcsr_At_mul_Bn(Z, M, np.ones(nrow * 3), 3); assert not Z.any()
+        A = fs.SparseBinaryMatrix(nrow, ncol, np.zeros(0, np.int32), np.zeros(0, np.int32))
+        Bl = fs.new_bsbm(A, 4); y = np.full(nrow, 7.0); fs.bsbm_A_mul_B(y, Bl, np.ones(ncol)); assert not y.any()
+        Cb = fs.cbcsr_from_sbm(A, 2); y[:] = 7.0; fs.cbcsr_A_mul_B(y, Cb, np.ones(ncol)); assert not y.any()
+    with pytest.raises(fs.FsbError):
+        fs.bcsr_A_mul_Bn(np.zeros(4), fs.BinaryCSR(1, 1, np.zeros(2, np.int32), np.zeros(0, np.int32)), np.ones(4), 0)
+
+
+# ------------------------------------------------------------------ device-side construction and generator
+def test_device_csr_build_is_bit_exact():
+    rng = np.random.default_rng(5)
+    nrow, ncol, nnz = 5000, 1234, 100000
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=9000)
+    rows[1000:1100] = rows[1000]; cols[1000:1100] = cols[1000]      # duplicate coordinates with different values
+    for v in (None, vals):
+        A = fs.SparseBinaryMatrix(nrow, ncol, rows, cols) if v is None else fs.SparseDoubleMatrix(nrow, ncol, rows, cols, v)
+        rp, cc, vv = fs.DeviceMatrix.of(A).download_csr()
+        orp, occ, ovv = oracle.csr_from_coo(nrow, rows, cols, v)
+        assert np.array_equal(rp, orp) and np.array_equal(cc, occ) and (v is None or np.array_equal(vv, ovv))
+
+
+def test_synth_generator_device_equals_host():
+    import torch
+    for dist, seed in [(0, 0x5EED0002), (1, 0x5EED0004)]:
+        n, nrow, ncol = 200000, 50000, 7001
+        hr, hc, hv = fs.synth_coo_host(seed, dist, n, nrow, ncol, with_vals=True)
+        M = fs.DeviceMatrix.synth(seed, dist, n, nrow, ncol, with_vals=True, keep_coo=True)
+        dr, dc, dv = (t.cpu().numpy() for t in M.coo)
+        assert np.array_equal(hr, dr) and np.array_equal(hc, dc) and np.array_equal(hv, dv)
+        rp, cc, vv = M.download_csr()
+        orp, occ, ovv = oracle.csr_from_coo(nrow, hr, hc, hv)
+        assert np.array_equal(rp, orp) and np.array_equal(cc, occ) and np.array_equal(vv, ovv)
+
+
+def test_row_shards_sum_to_full_product():
+    import torch
+    M = fs.DeviceMatrix.synth(11, 1, 300000, 40000, 5000, with_vals=True)
+    rp, _, _ = M.download_csr()
+    R = 8
+    X = torch.randn(M.ncol * R, dtype=torch.float64, device="cuda"); Xt = torch.randn(M.nrow * R, dtype=torch.float64, device="cuda")
+    Y = M.spmm(X, R); Z = M.spmm_t(Xt, R)
+    b = fs.partition_rows(rp, 3)
+    Zsum = torch.zeros_like(Z)
+    for p in range(3):
+        S = M.row_slice(b[p], b[p + 1])
+        assert torch.equal(S.spmm(X, R), Y[b[p] * R: b[p + 1] * R])          # A x needs no exchange: shards are row slabs
+        Zsum += S.spmm_t(Xt[b[p] * R: b[p + 1] * R].contiguous(), R)             # A' x: partials that an allreduce would sum
+    assert torch.allclose(Zsum, Z, rtol=1e-12, atol=1e-10)
+
+
+# ------------------------------------------------------------------ solver
+def _cg_setup(name="sbm_100_50", bs=8):
+    g = golden(name)
+    nrow, ncol = int(g["nrow"]), int(g["ncol"])
+    A = fs.new_sbm(nrow, ncol, g["rows"].size, g["rows"].copy(), g["cols"].copy())
+    fs.sort_sbm(A)
+    B = fs.new_bsbm(A, bs)
+    fs.transpose(A)
+    Bt = fs.new_bsbm(A, bs)
+    return g, nrow, ncol, B, Bt
+
+
+def test_cg_matches_reference():     # test_sparse.c:560-608 + SURVEY 8c extras
+    g, nrow, ncol, B, Bt = _cg_setup()
+    b = tvec(ncol); x = np.zeros(ncol)
+    y = np.zeros(ncol); tmp = np.zeros(nrow)
+    fs.bsbm_AtA(y, B, Bt, b, tmp, 5.0); assert_close(y, g["AtA_b"], 400.0, what="bsbm_AtA")
+    it = fs.bsbm_cg(x, B, Bt, b, 5.0, 1e-6)
+    assert it == 15 and abs(x[0] - 0.0638578) < 1e-4 and abs(x[1] + 0.0302702) < 1e-4 and abs(x[49] + 0.0284737361861) < 1e-9
+    assert np.max(np.abs(x - g["cg_x"])) < 1e-9
+    rows, cols = g["rows"], g["cols"]
+    resid = oracle.coo_mul(nrow, rows, cols, None, oracle.coo_mul(nrow, rows, cols, None, x), transpose=True, ncol=ncol) + 5.0 * x - b
+    assert np.linalg.norm(resid) < 1e-5
+    X2 = np.zeros(ncol * 2); it2 = fs.bsbm_cg2(X2, B, Bt, g["cg2_B"], 5.0, 1e-6)
+    assert it2 == 13 and np.max(np.abs(X2.reshape(ncol, 2) - g["cg2_X"])) < 1e-9
+    assert abs(X2[0] - 0.0638578) < 1e-4 and abs(X2[2] + 0.0302702) < 1e-4
+    with pytest.raises(fs.FsbError):       # cg.h:32-36 shape check
+        fs.bsbm_cg(x, B, B, b, 5.0, 1e-6)
+
+
+@pytest.mark.parametrize("R", [2, 5, 32])
+def test_block_cg_n_rhs(R):
+    """R-RHS block CG (no reference counterpart): oracle = bsbm_cg per column at tight tolerance + residual."""
+    g, nrow, ncol, B, Bt = _cg_setup("rand_bin_300_70", bs=32)
+    rng = np.random.default_rng(R)
+    Bm = f64(rng.standard_normal((ncol, R))); lam = 3.0
+    X = np.zeros(ncol * R); it = fs.bsbm_cgn(X, B, Bt, Bm, R, lam, 1e-9)
+    X = X.reshape(ncol, R)
+    assert 0 < it <= ncol
+    hr, hc = g["hil_rows"], g["hil_cols"]
+    Ao = oracle.blocked_from_coo(nrow, ncol, 32, hr, hc); Ato = oracle.blocked_from_coo(ncol, nrow, 32, hc, hr)
+    for k in range(R):
+        xo = np.zeros(ncol); O.fso_blocked_cg(dp(xo), Ao.ref(), Ato.ref(), dp(f64(Bm[:, k])), lam, 1e-11)
+        assert np.max(np.abs(X[:, k] - xo)) <= 1e-7 * max(1.0, np.max(np.abs(xo))), f"column {k}"
+        r = oracle.coo_mul(nrow, hr, hc, None, oracle.coo_mul(nrow, hr, hc, None, X[:, k]), transpose=True, ncol=ncol) + lam * X[:, k] - Bm[:, k]
+        assert np.linalg.norm(r) <= 1e-7 * np.linalg.norm(Bm[:, k])
+
+
+def test_cg_on_csr_handle_with_cached_transpose():
+    import torch
+    M = fs.DeviceMatrix.synth(3, 0, 200000, 20000, 2000)
+    R = 8
+    Bm = torch.randn(M.ncol * R, dtype=torch.float64, device="cuda")
+    X, it = M.cg(Bm, R, lam=15.0, tol=1e-8)
+    KX = M.ata(X, R, lam=15.0)
+    rel = (KX - Bm).reshape(M.ncol, R).norm(dim=0) / Bm.reshape(M.ncol, R).norm(dim=0)
+    assert it > 0 and float(rel.max()) < 1e-7
+    assert torch.allclose(M.ata(X, R, lam=15.0, mode=1), KX, rtol=1e-11, atol=1e-9)      # fused scatter mode agrees
+
+
+def test_linalg_reductions():        # test_sparse.c:511-544
+    x = np.array([0.12, -0.82, 1.3, 0.5]); y = np.array([6.12, 0.19, 3.4, -4.1])
+    assert abs(fs.pnormsq(x, 4) - 2.6268) < 1e-8 and abs(fs.pnormsq(y, 4) - 65.8605) < 1e-8 and abs(fs.pdot(x, y, 4) - 2.9486) < 1e-8
+    o = np.zeros(3); fs.pouter2(o, x, 2)
+    assert np.max(np.abs(o - [0.12 * 0.12 + 1.3 * 1.3, 0.82 * 0.82 + 0.5 * 0.5, 0.12 * -0.82 + 1.3 * 0.5])) < 1e-12
+    X = np.array([0.95, 0.9, 0.16, 0.46, 0.86, 0.29]); Y = np.array([0.9695, 0.6678, 0.277, 0.1908, 1.108, 0.7632])
+    d = np.zeros(3); fs.pdot2sym(d, X, Y, 3); assert np.max(np.abs(d - [1.918225, 0.910116, 1.32129])) < 1e-8
+    S = np.zeros(4); fs.solve2sym(S, [0.59, 1.34, 0.86], [-1.21, 1.91, -0.82, 0.03])
+    assert np.max(np.abs(S - [-64.0, 42.5, -22.05098039, 14.1745098])) < 1e-8
+    gl = golden("linalg"); n = gl["x"].size
+    assert abs(fs.pdot(gl["x"], gl["y"], n) - gl["dot"]) < 1e-10 and abs(fs.dist(gl["x"], gl["y"], n) - gl["dist"]) < 1e-10
+    d = np.zeros(3); fs.pdot2sym(d, gl["X"], gl["Y"], n); assert np.max(np.abs(d - gl["dot2sym"])) < 1e-10
+
+
+# ------------------------------------------------------------------ BASELINE.json full size: size-independent properties
+def test_full_size_c2_properties():
+    """C2: binary CSR 10M x 1M, 200M nnz, R = 32.  Checks: (i) a slab of rows against the oracle,
+    (ii) checksum of checksums sum_r Y[r,:] == sum_c count[c] X[c,:], (iii) linearity,
+    (iv) A'(A X) two-pass == fused scatter == <AX, AX> identity."""
+    import torch
+    N, F, NNZ, R = 10_000_000, 1_000_000, 200_000_000, 32
+    M = fs.DeviceMatrix.synth(0x5EED0002, 0, NNZ, N, F, keep_coo=True)
+    cols_t = M.coo[1]
+    cnt = torch.bincount(cols_t.long(), minlength=F).double()
+    del M.coo
+    c = torch.arange(F, device="cuda", dtype=torch.float64)[:, None]; k = torch.arange(R, device="cuda", dtype=torch.float64)[None, :]
+    X = torch.sin(7.0 * c + 17.0 * k + 0.3).reshape(-1).contiguous()
+    Y = M.spmm(X, R)
+    # (i) first 3000 rows against the oracle
+    S = M.row_slice(0, 3000); rp, cc, _ = S.download_csr()
+    want = oracle.csr_mul(3000, rp, cc, None, X.cpu().numpy(), R)
+    assert_close(Y[: 3000 * R].cpu().numpy(), want, 64.0, what="C2 row slab")
+    # (ii) column sums
+    colsum = Y.reshape(N, R).sum(0); ref = (cnt[:, None] * X.reshape(F, R)).sum(0)
+    assert torch.allclose(colsum, ref, rtol=1e-9, atol=1e-3)
+    # (iii) linearity
+    X2 = torch.cos(3.0 * c - 5.0 * k).reshape(-1).contiguous()
+    Y2 = M.spmm(X2, R); Y12 = M.spmm(X + 2.0 * X2, R)
+    assert torch.allclose(Y12, Y + 2.0 * Y2, rtol=1e-12, atol=1e-10)
+    del Y2, Y12
+    # (iv) <X, A'A X> == <AX, AX>, per column
+    Z = M.ata(X, R)
+    lhs = (X.reshape(F, R) * Z.reshape(F, R)).sum(0); rhs = (Y.reshape(N, R) ** 2).sum(0)
+    assert torch.allclose(lhs, rhs, rtol=1e-10)
