@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfastsparse_b200.so")
+# FSB_LIB selects an experiment build (tools/sweep.py); the default is the product library
+LIB_PATH = os.environ.get("FSB_LIB") or os.path.join(HERE, "lib", "libfastsparse_b200.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_long_p = C.POINTER(C.c_long)

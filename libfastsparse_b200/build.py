@@ -58,6 +58,34 @@ def _compile(src: str, hdr_time: float, force: bool, verbose: bool) -> str:
     return obj
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment build: lib/libfastsparse_b200_<name>.so with extra -D flags (selected at run time by FSB_LIB)."""
+    objdir = os.path.join(LIBDIR, "obj_" + name)
+    os.makedirs(objdir, exist_ok=True)
+    out = os.path.join(LIBDIR, f"libfastsparse_b200_{name}.so")
+    objs = []
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if src.endswith(".cpp"):
+            cmd = [HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-I", INCLUDE, "-c", path, "-o", obj]
+        else:
+            cmd = [NVCC, *ARCH, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", path, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"compile failed: {src}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, SOURCES))
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-ccbin", HOST_CXX, "-o", out, *objs, "-cudart", "static", "-Xcompiler", "-fopenmp",
+                        "-ldl", "-lgomp"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     hdr_time = _deps_mtime()
@@ -75,4 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

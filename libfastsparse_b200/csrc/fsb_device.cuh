@@ -41,10 +41,18 @@ template <> struct XLoad<2> {
     asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
   }
 };
+#ifndef FSB_X_EVICT_LAST
+#define FSB_X_EVICT_LAST 1
+#endif
 template <> struct XLoad<4> {
   static __device__ __forceinline__ void ld(double* v, const double* p) {
+#if FSB_X_EVICT_LAST
     asm volatile("ld.global.nc.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#else
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+#endif
   }
 };
 

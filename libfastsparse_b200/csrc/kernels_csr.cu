@@ -31,13 +31,21 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// compile-time experiment knobs (tools/variants.sh builds one .so per setting)
+#ifndef FSB_SPMM_U
+#define FSB_SPMM_U 4          // gathers in flight per lane
+#endif
+#ifndef FSB_SPMM_MINBLOCKS
+#define FSB_SPMM_MINBLOCKS 1  // __launch_bounds__ min CTAs per SM (register cap)
+#endif
+
 template <int TW, int G, int VEC, bool VALS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FSB_SPMM_MINBLOCKS)
 csr_spmm_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                 const double* __restrict__ vals, const double* __restrict__ X,
                 double* __restrict__ Y, int R, int col0, int ncols) {
   constexpr int NSUB = TW / G;            // sub-groups (nonzeros in flight) per team
-  constexpr int U = (G >= 4) ? 4 : G;     // gathers in flight per lane
+  constexpr int U = (G >= FSB_SPMM_U) ? FSB_SPMM_U : G;     // gathers in flight per lane
   const long long gt = (long long)blockIdx.x * kThreads + threadIdx.x;
   const int row = (int)(gt / TW);
   if (row >= nrow) return;                // whole team leaves together
@@ -223,7 +231,10 @@ bool dispatch_fused(int tw, int g, const fsb_matrix* A, double* dY, const double
 // team width from the mean row length: enough sub-groups to cover a row in a couple
 // of steps without leaving most of them idle
 int pick_tw(int g, double avg_nnz) {
-  int want = pow2_floor(std::max(1, (int)(avg_nnz / 2.0)));
+  // wide gathers (g >= 8): two sub-groups per ~20-entry row measured best on B200
+  // (profiles/r1_sweep_c2.md); narrow gathers want more lanes on the row's index stream
+  const double per_sub = g >= 8 ? 8.0 : 2.0;
+  int want = pow2_floor(std::max(1, (int)(avg_nnz / per_sub)));
   int ns = std::min(want, 32 / g);
   return g * std::max(ns, 1);
 }
