@@ -118,6 +118,9 @@ int fsb_ata_host(fsb_matrix_t A, double* Y, const double* X, int R, double lambd
 /* y = At (A x) + lambda x with an explicitly stored transpose, as cg.h:9-22 */
 int fsb_ata_pair_dev(fsb_matrix_t A, fsb_matrix_t At, double* dY, const double* dX,
                      int R, double lambda, double* dTmp, void* stream);
+/* host operands; tmp (nrow*R doubles, may be NULL) receives A x like the reference's scratch */
+int fsb_ata_pair_host(fsb_matrix_t A, fsb_matrix_t At, double* Y, const double* X, int R,
+                      double lambda, double* tmp);
 
 /* --------------------------------------------------------------- solver */
 /* Block conjugate gradient for (A'A + lambda I) X = B with R right-hand sides,
@@ -136,6 +139,10 @@ int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const double* dB, in
 /* G[Ra][Rb] = Xa' Xb over n rows (row-major result, device pointers; out on host).
  * Replaces pnormsq/pnormsq2/pouter2/pdot/pdot2sym linalg.h:15-73. */
 int fsb_gram_dev(double* G_host, const double* dXa, const double* dXb, long n, int R, void* stream);
+/* same with HOST operands (the drop-in linalg.h path): copies Xa, Xb in, reduces on the GPU */
+int fsb_gram_host(double* G, const double* Xa, const double* Xb, long n, int R);
+/* *out = sqrt(sum (x[i]-y[i])^2) on the GPU, host operands.  Replaces dist linalg.h:6-13. */
+int fsb_dist_host(double* out, const double* x, const double* y, long n);
 
 /* ------------------------------------------------------------ multi-GPU */
 /* One process per GPU.  Rank 0 calls fsb_comm_unique_id, the bytes travel by any

@@ -469,11 +469,11 @@ def cbcsr_A_mul_B(y, A, x):                                   # cbcsr.h:76-106
 
 # ----------------------------------------------------------------------------- linalg.h (reductions run on the GPU)
 def _gram(Xa, Xb, n, R):
-    import torch
     G = np.zeros((R, R), np.float64)
-    ta = torch.from_numpy(_f64(Xa).reshape(-1)[: n * R]).cuda()
-    tb = ta if Xb is Xa else torch.from_numpy(_f64(Xb).reshape(-1)[: n * R]).cuda()
-    check(lib().fsb_gram_dev(_dp(G), ta.data_ptr(), tb.data_ptr(), n, R, _torch_stream()))
+    a = _f64(Xa).reshape(-1)
+    b = a if Xb is Xa else _f64(Xb).reshape(-1)
+    assert a.size >= n * R and b.size >= n * R
+    check(lib().fsb_gram_host(_dp(G), _dp(a), _dp(b), n, R))
     return G
 
 
@@ -510,8 +510,9 @@ def solve2sym(X, A, RHS):                                     # linalg.h:77-88 (
 
 
 def dist(x, y, n):                                            # linalg.h:6-13
-    d = _f64(x)[:n] - _f64(y)[:n]
-    return float(np.sqrt(_gram(d, d, n, 1)[0, 0]))
+    out = C.c_double(0.0)
+    check(lib().fsb_dist_host(C.byref(out), _dp(_f64(x)), _dp(_f64(y)), n))
+    return out.value
 
 
 # ----------------------------------------------------------------------------- cg.h
@@ -521,16 +522,11 @@ def _check_pair(A, At):
 
 
 def bsbm_AtA(y, A, At, x, tmp, lam):                          # cg.h:9-22
-    import torch
     _check_pair(A, At)
-    tx = torch.from_numpy(_f64(x)[: A.ncol]).cuda()
-    ty = torch.empty(A.ncol, dtype=torch.float64, device="cuda")
-    tt = torch.empty(A.nrow, dtype=torch.float64, device="cuda")
-    st = _torch_stream()
-    check(lib().fsb_ata_pair_dev(A._dev(), At._dev(), ty.data_ptr(), tx.data_ptr(), 1, float(lam), tt.data_ptr(), st))
-    _out(y, A.ncol)[: A.ncol] = ty.cpu().numpy()
-    if tmp is not None:
-        tmp[: A.nrow] = tt.cpu().numpy()
+    x = _f64(x)
+    assert x.size >= A.ncol
+    check(lib().fsb_ata_pair_host(A._dev(), At._dev(), _dp(_out(y, A.ncol)), _dp(x), 1, float(lam),
+                                  _dp(_out(tmp, A.nrow)) if tmp is not None else None))
 
 
 def bsbm_cgn(X, A, At, B, ncol, lam, tol, max_iter=0):

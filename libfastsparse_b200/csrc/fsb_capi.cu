@@ -440,6 +440,22 @@ int fsb_ata_host(fsb_matrix_t A, double* Y, const double* X, int R, double lambd
   return FSB_OK;
 }
 
+int fsb_ata_pair_host(fsb_matrix_t A, fsb_matrix_t At, double* Y, const double* X, int R, double lambda, double* tmp) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !At || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_ata_pair_host: bad argument");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  const size_t b = (size_t)A->ncol * R * 8, bt = (size_t)A->nrow * R * 8;
+  FSB_TRY(stage_reserve(std::max<size_t>(b, 8), std::max<size_t>(b, 8)));
+  double* dTmp = nullptr;
+  FSB_TRY(fsb_matrix_scratch(A, std::max<size_t>(bt, 8), &dTmp));
+  if (b) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, b, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_ata_pair_dev(A, At, g_stage.dY, g_stage.dX, R, lambda, dTmp, g_stream));
+  if (b) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, b, cudaMemcpyDeviceToHost, g_stream));
+  if (tmp && bt) FSB_CUDA(cudaMemcpyAsync(tmp, dTmp, bt, cudaMemcpyDeviceToHost, g_stream));
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
 void fsb_die(const char* where) {
   fprintf(stderr, "libfastsparse_b200: %s: %s\n", where ? where : "error", tl_error);
   exit(1);

@@ -292,3 +292,52 @@ extern "C" int fsb_gram_dev(double* G_host, const double* dXa, const double* dXb
   cudaFree(dG); cudaFree(dPart);
   return rc;
 }
+
+namespace {
+__global__ void diff_kernel(double* __restrict__ d, const double* __restrict__ x, const double* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = x[i] - y[i];
+}
+}  // namespace
+
+extern "C" int fsb_gram_host(double* G, const double* Xa, const double* Xb, long n, int R) {
+  FSB_TRY(fsb_require_device());
+  if (!G || !Xa || !Xb || n < 0 || R < 1 || R > 32) return fsb_set_error(FSB_EINVAL, "fsb_gram_host: bad argument");
+  cudaStream_t st = fsb_default_stream();
+  const size_t bytes = std::max<size_t>((size_t)n * R, 1) * 8;
+  double *da = nullptr, *db = nullptr;
+  FSB_CUDA(cudaMalloc(&da, bytes));
+  int rc = FSB_OK;
+  cudaError_t e = cudaMemcpyAsync(da, Xa, (size_t)n * R * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && Xb != Xa) {
+    e = cudaMalloc(&db, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db, Xb, (size_t)n * R * 8, cudaMemcpyHostToDevice, st);
+  }
+  if (e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_gram_host staging", __FILE__, __LINE__);
+  if (rc == FSB_OK) rc = fsb_gram_dev(G, da, db ? db : da, n, R, (void*)st);
+  cudaFree(da); cudaFree(db);
+  return rc;
+}
+
+extern "C" int fsb_dist_host(double* out, const double* x, const double* y, long n) {
+  FSB_TRY(fsb_require_device());
+  if (!out || !x || !y || n < 0) return fsb_set_error(FSB_EINVAL, "fsb_dist_host: bad argument");
+  cudaStream_t st = fsb_default_stream();
+  const size_t bytes = std::max<size_t>((size_t)n, 1) * 8;
+  double *dx = nullptr, *dy = nullptr;
+  FSB_CUDA(cudaMalloc(&dx, bytes));
+  cudaError_t e = cudaMalloc(&dy, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "fsb_dist_host staging", __FILE__, __LINE__);
+  if (rc == FSB_OK && n > 0) {
+    diff_kernel<<<grid_for(n), 256, 0, st>>>(dx, dx, dy, n);
+    fsb_count_launch();
+  }
+  double g = 0.0;
+  if (rc == FSB_OK) rc = fsb_gram_dev(&g, dx, dx, n, 1, (void*)st);
+  cudaFree(dx); cudaFree(dy);
+  if (rc == FSB_OK) *out = sqrt(g);
+  return rc;
+}
