@@ -181,7 +181,8 @@ def run_ours(args):
     X = torch.sin(7.0 * c + 17.0 * k + 0.3).reshape(-1).contiguous()
     Y = torch.empty(nrow * R, dtype=torch.float64, device="cuda")
     if args.tune:
-        tw, g, vec, slabs = (int(v) for v in args.tune.split(","))
+        algo, tw, g, vec, slabs, rb = (int(v) for v in args.tune.split(","))
+        fs.check(fs.lib().fsb_tune_csr_algo(algo, rb, 0))
         fs.check(fs.lib().fsb_tune_csr_spmm(tw, g, vec, slabs))
 
     def barrier():
@@ -278,7 +279,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--tune", default="", help="tw,g,vec,slabs override of the SpMM launch heuristic")
+    ap.add_argument("--tune", default="", help="algo,tw,g,vec,slabs,rb override of the SpMM launch heuristic (see tools/sweep.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -227,6 +227,9 @@ void fsb_die(const char* where);
  * g = lanes per gathered dense row, vec = doubles per lane (1, 2 or 4), slabs =
  * column passes over the dense operand.  Used by tools/sweep.py and the tests. */
 int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs);
+/* algo: 0 automatic, 1 team-per-row kernel, 2 staged row-block kernel; rows_per_cta and
+ * cap_mult (staging capacity = cap_mult * mean entries per CTA) are 0 for automatic */
+int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult);
 
 /* ------------------------------------------ synthetic inputs (bench) */
 /* Counter-based generator: entry j of the COO is a pure function of (seed, j),

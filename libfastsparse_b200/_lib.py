@@ -89,6 +89,7 @@ _SIGS = {
     "fsb_cache_clear": (None, []),
     "fsb_die": (None, [C.c_char_p]),
     "fsb_tune_csr_spmm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fsb_tune_csr_algo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fsb_synth_coo_dev": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsb_synth_coo_host": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),
 }

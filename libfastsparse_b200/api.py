@@ -27,6 +27,7 @@ __all__ = [
     "new_cbcsr", "cbcsr_from_sbm", "cbcsr_A_mul_B", "cbcsr_A_mul_Bn", "bsbm_AtA", "bsbm_cg", "bsbm_cg2", "bsbm_cgn",
     "pnormsq", "pnormsq2", "pouter2", "pdot", "pdot2sym", "solve2sym", "dist", "ceilPower2", "xy2d", "d2xy", "row_xy2d",
     "row_d2xy", "quickSort", "quickSortD", "partition_rows", "synth_coo_host", "device_count", "launch_count",
+    "comm_init_from_torch", "comm_finalize", "allreduce_sum",
 ]
 
 
@@ -666,3 +667,30 @@ class DeviceMatrix:
             self.free()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------- multi-GPU plumbing
+def comm_init_from_torch():
+    """Create the library's NCCL communicator over the ranks of the current torch.distributed
+    process group (one process per GPU): rank 0 makes the unique id, torch broadcasts the bytes."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(lib().fsb_comm_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    check(lib().fsb_comm_init(world, rank, raw))
+    return world, rank
+
+
+def comm_finalize():
+    check(lib().fsb_comm_finalize())
+
+
+def allreduce_sum(t):
+    """In-place sum-allreduce of a float64 CUDA tensor over the library communicator."""
+    check(lib().fsb_allreduce_sum_dev(t.data_ptr(), t.numel(), _torch_stream()))
+    return t

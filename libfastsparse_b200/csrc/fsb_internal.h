@@ -73,6 +73,10 @@ int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st);
 // tuning override for the sweep tool: TW, G, VEC, slabs (0 = heuristic)
 void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
+// ---- kernels_csr_staged.cu
+int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
+                               int g, int vec, cudaStream_t st);
+void fsb_csr_staged_set_tuning(int rows_per_cta, int cap_mult);
 
 // ---- kernels_cbcsr.cu / kernels_blocked.cu
 int fsb_launch_cbcsr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);

@@ -166,6 +166,7 @@ __global__ void scale_copy_kernel(double* __restrict__ Y, const double* __restri
 }
 
 int g_tw = 0, g_g = 0, g_vec = 0, g_slabs = 0;
+int g_algo = 0;   // 0 = automatic, 1 = team-per-row kernel (this file), 2 = staged row-block kernel
 
 inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 inline int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p <<= 1; return p; }
@@ -245,6 +246,13 @@ void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs) {
   g_tw = tw; g_g = g; g_vec = vec; g_slabs = slabs;
 }
 
+extern "C" int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult) {
+  if (algo < 0 || algo > 2 || rows_per_cta < 0 || cap_mult < 0) return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_algo: bad argument");
+  g_algo = algo;
+  fsb_csr_staged_set_tuning(rows_per_cta, cap_mult);
+  return FSB_OK;
+}
+
 extern "C" int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs) {
   auto pow2 = [](int x) { return x == 0 || (x > 0 && x <= 32 && (x & (x - 1)) == 0); };
   if (!pow2(tw) || !pow2(g) || !(vec == 0 || vec == 1 || vec == 2 || vec == 4) || slabs < 0)
@@ -267,8 +275,13 @@ int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R
   if (g_g && g_g >= g && g_g <= 32) g = g_g;
   int tw = pick_tw(g, A->avg_row_nnz);
   if (g_tw && g_tw >= g && g_tw <= 32) tw = g_tw;
+  const int algo = g_algo ? g_algo : 2;
   for (int col0 = 0; col0 < R; col0 += per_pass) {
     const int ncols = std::min(per_pass, R - col0);
+    if (algo == 2) {
+      FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dX, R, col0, ncols, g, vec, st));
+      continue;
+    }
     if (!dispatch_spmm(tw, g, vec, A, dY, dX, R, col0, ncols, st))
       return fsb_set_error(FSB_EINVAL, "spmm: no kernel for TW=%d G=%d VEC=%d", tw, g, vec);
     FSB_KERNEL_CHECK();

@@ -1,0 +1,200 @@
+// kernels_csr_staged.cu -- CSR SpMM / SpMV, "staged row block" kernel (sm_100a).
+//
+// Same products as kernels_csr.cu (bcsr_A_mul_B* csr.h:149-302, csr_A_mul_B* csr.h:425-465).
+// The first kernel (one team per row) is latency bound on B200: ncu shows DRAM at ~53 %
+// with long-scoreboard stalls, because every row is a chain of three dependent global
+// loads (row_ptr -> cols -> X rows) and each team has little in flight
+// (profiles/r1a_ncu_c2_spmm_details.md).  This kernel breaks the chain:
+//
+//   * a CTA owns RB consecutive rows; it first copies their row_ptr slice and the whole
+//     contiguous run of column indices (and values) into SHARED MEMORY with fully
+//     coalesced loads -- one exposed latency per RB rows instead of per row;
+//   * then every sub-group of G lanes walks its rows with the indices already on chip:
+//     U independent gathers of the dense operand are issued back to back (each lane one
+//     vector LDG of VEC doubles; VEC = 4 is a single 256-bit LDG.E.256), so a warp keeps
+//     (32/G)*U X rows in flight;
+//   * a sub-group sums a row's terms strictly in stored order, i.e. in the reference's
+//     own order: the binary product is bit-identical to the serial reference;
+//   * rows too long for the staging buffer are processed by the whole CTA (fixed
+//     chunking + shared-memory reduction, still deterministic).
+#include <algorithm>
+
+#include "fsb_device.cuh"
+#include "fsb_internal.h"
+
+using namespace fsbdev;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kLongRow = 2048;   // rows at least this long are split across the CTA
+
+#ifndef FSB_STAGED_U
+#define FSB_STAGED_U 4
+#endif
+
+template <int G, int VEC, bool VALS, bool FROM_SMEM>
+__device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
+                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok) {
+  constexpr int U = FSB_STAGED_U;
+  for (int i = s; i < e; i += U) {
+    double xr[U][VEC];
+    double vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = i + u;
+      if (idx < e && col_ok) {
+        const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
+        if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
+        XLoad<VEC>::ld(xr[u], xbase + (long long)c * R);
+      } else {
+        if (VALS) vv[u] = 0.0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) xr[u][v] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = VALS ? fma(xr[u][v], vv[u], acc[v]) : acc[v] + xr[u][v];
+  }
+}
+
+template <int G, int VEC, bool VALS>
+__global__ void __launch_bounds__(kThreads)
+csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                       const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                       int R, int col0, int ncols, int RB, int CAP) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
+  // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
+  int* s_rp = reinterpret_cast<int*>(smem_raw);
+  unsigned char* body = smem_raw + (((size_t)(RB + 1) * 4 + 15) & ~(size_t)15);
+  double* s_vals = reinterpret_cast<double*>(body);
+  int* s_cols = reinterpret_cast<int*>(body + (VALS ? (size_t)CAP * 8 : 0));
+  double* s_red = reinterpret_cast<double*>(body);
+
+  constexpr int NT = kThreads / G;   // sub-groups per CTA
+  const int tid = threadIdx.x;
+  const int team = tid / G, l = tid & (G - 1);
+  const int r0 = blockIdx.x * RB;
+  const int nr = min(RB, nrow - r0);
+  const bool col_ok = l * VEC < ncols;
+  const double* xbase = X + col0 + l * VEC;
+
+  for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptr + r0 + i);
+  __syncthreads();
+  const int base = s_rp[0];
+  const int total = s_rp[nr] - base;
+
+  if (total <= CAP) {
+    for (int i = tid; i < total; i += kThreads) {
+      s_cols[i] = ld_stream_s32(cols + base + i);
+      if (VALS) s_vals[i] = ld_stream_f64(vals + base + i);
+    }
+    __syncthreads();
+    for (int r = team; r < nr; r += NT) {
+      double acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok);
+      if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
+    }
+    return;
+  }
+
+  // overflow: at least one long row in this block.  Short rows go to sub-groups as usual
+  // (indices read from global memory); long rows are split across all sub-groups.
+  __syncthreads();   // s_rp is read below while s_red (aliased with vals/cols, not s_rp) is written
+  for (int r = 0; r < nr; ++r) {
+    const int s = s_rp[r], e = s_rp[r + 1];
+    if (e - s >= kLongRow) {
+      const int chunk = (e - s + NT - 1) / NT;
+      const int cs = min(e, s + team * chunk), ce = min(e, cs + chunk);
+      double acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, col_ok);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
+      __syncthreads();
+      if (team == 0 && col_ok) {
+        double tot[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) tot[v] = 0.0;
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) tot[v] += s_red[(t * G + l) * VEC + v];
+        YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, tot);
+      }
+      __syncthreads();
+    } else if (r % NT == team) {
+      double acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, col_ok);
+      if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
+    }
+  }
+}
+
+int g_rb = 0, g_cap_mult = 0;
+
+inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <int G, int VEC, bool VALS>
+int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
+  auto kern = csr_spmm_staged_kernel<G, VEC, VALS>;
+  size_t body = std::max((size_t)CAP * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging or long-row reduction
+  size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
+  if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
+  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP);
+  return FSB_OK;
+}
+
+template <int G, int VEC>
+int launch_v(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
+  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st)
+                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+}
+
+template <int G>
+int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
+  switch (vec) {
+    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+  }
+}
+
+}  // namespace
+
+void fsb_csr_staged_set_tuning(int rb, int cap_mult) { g_rb = rb; g_cap_mult = cap_mult; }
+
+// one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
+int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
+                               int g, int vec, cudaStream_t st) {
+  // rows per CTA: enough rows that every sub-group gets a few, bounded so that the index
+  // run (~avg_nnz * RB entries) stays a small shared-memory footprint (several CTAs per SM)
+  const int nt = kThreads / g;
+  int rb = g_rb ? g_rb : std::max(nt * 4, 128);
+  const double avg = std::max(A->avg_row_nnz, 1.0);
+  const double budget = A->has_vals ? 2048.0 : 4096.0;     // staged entries per CTA (12 or 4 bytes each)
+  while (rb > nt && rb > 8 && avg * rb > budget) rb /= 2;
+  rb = std::max(rb, 1);
+  int cap = (int)std::min<double>(avg * rb * (g_cap_mult ? g_cap_mult : 1.5) + 256, 3.0 * budget);
+  cap = std::max((cap + 63) & ~63, 512);
+  int rc;
+  switch (g) {
+    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+  }
+  FSB_TRY(rc);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}

@@ -138,8 +138,34 @@ def _random_case(rng, nrow, ncol, nnz, long_row=0):
     return rows, cols, rng.random(nnz)
 
 
+@pytest.fixture(params=[1, 2], ids=["team-kernel", "staged-kernel"])
+def csr_algo(request):
+    """Run a test once per CSR SpMM kernel (fsb_tune_csr_algo), then restore the automatic choice."""
+    fs.check(fs.lib().fsb_tune_csr_algo(request.param, 0, 0))
+    yield request.param
+    fs.check(fs.lib().fsb_tune_csr_algo(0, 0, 0))
+
+
+def test_staged_kernel_is_bit_identical_to_serial_reference_order():
+    """The staged kernel sums each row in stored order: binary products must equal the oracle's
+    in-order sums exactly, including rows long enough to take the split path."""
+    rng = np.random.default_rng(42)
+    nrow, ncol, nnz = 5000, 900, 60000
+    rows = rng.integers(0, nrow, nnz, dtype=np.int32); cols = rng.integers(0, ncol, nnz, dtype=np.int32)
+    rp, cc, _ = oracle.csr_from_coo(nrow, rows, cols)
+    M = fs.BinaryCSR(nrow, ncol, rp, cc)
+    fs.check(fs.lib().fsb_tune_csr_algo(2, 0, 0))
+    try:
+        for R in (1, 4, 32):
+            X = f64(rng.standard_normal((ncol, R)))
+            Y = np.zeros(nrow * R); fs.bcsr_A_mul_Bn(Y, M, X, R)
+            assert np.array_equal(Y, oracle.csr_mul(nrow, rp, cc, None, X, R).reshape(-1)), f"R={R}"
+    finally:
+        fs.check(fs.lib().fsb_tune_csr_algo(0, 0, 0))
+
+
 @pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 8, 16, 17, 31, 32, 33, 64, 100])
-def test_csr_products_ragged(R):
+def test_csr_products_ragged(R, csr_algo):
     rng = np.random.default_rng(R)
     nrow, ncol, nnz = 3001, 777, 40000
     rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=5000)

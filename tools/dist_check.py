@@ -1,0 +1,76 @@
+"""Multi-GPU correctness check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/dist_check.py
+
+Every rank builds the same synthetic matrix, keeps only its nnz-balanced row shard, and the
+sharded A x / A' x / A'(A x) / block-CG results (with the library's NCCL allreduce of the
+A'(...) partials) are compared against the single-GPU results of the full matrix."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import libfastsparse_b200 as fs  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fs.comm_init_from_torch()
+    out = {"world": world}
+    ok = True
+    for with_vals, R in [(False, 32), (True, 1), (True, 8)]:
+        nrow, ncol, nnz = 400_000, 50_000, 8_000_000
+        full = fs.DeviceMatrix.synth(4242, 1, nnz, nrow, ncol, with_vals=with_vals)
+        rp, _, _ = full.download_csr()
+        b = fs.partition_rows(rp, world)
+        r0, r1 = int(b[rank]), int(b[rank + 1])
+        shard = full.row_slice(r0, r1)
+        shard.set_row_sharded(True)
+        g = torch.Generator(device="cuda"); g.manual_seed(7)
+        X = torch.randn(ncol * R, dtype=torch.float64, device="cuda", generator=g)
+        Xt = torch.randn(nrow * R, dtype=torch.float64, device="cuda", generator=g)
+        B = torch.randn(ncol * R, dtype=torch.float64, device="cuda", generator=g)
+        tag = f"{'dbl' if with_vals else 'bin'}_R{R}"
+        # A x: no collective, the shard's slab is bit-identical to the full product's rows
+        Y = full.spmm(X, R)
+        out[tag + "_Ax_slab_equal"] = bool(torch.equal(shard.spmm(X, R), Y[r0 * R: r1 * R]))
+        # A' x: allreduce of partials inside the library
+        Z = full.spmm_t(Xt, R)
+        Zs = shard.spmm_t(Xt[r0 * R: r1 * R].contiguous(), R)
+        out[tag + "_Atx_err"] = float((Zs - Z).abs().max() / Z.abs().max())
+        # A'(A x) + lambda x, both modes
+        K = full.ata(X, R, lam=2.5)
+        for mode in (0, 1):
+            Ks = shard.ata(X, R, lam=2.5, mode=mode)
+            out[f"{tag}_AtA_mode{mode}_err"] = float((Ks - K).abs().max() / K.abs().max())
+        # block CG on the shard vs on the full matrix
+        Xf, itf = full.cg(B, R, lam=15.0, tol=1e-8)
+        Xs, its = shard.cg(B, R, lam=15.0, tol=1e-8)
+        out[tag + "_cg_iters"] = [itf, its]
+        out[tag + "_cg_err"] = float((Xs - Xf).abs().max() / Xf.abs().max())
+        ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12 and out[tag + "_cg_err"] < 1e-6 and abs(itf - its) <= max(2, itf // 20)
+        ok &= all(out[f"{tag}_AtA_mode{m}_err"] < 1e-12 for m in (0, 1))
+        # all ranks must hold the same allreduced result
+        chk = Zs.sum().reshape(1).clone(); lo = chk.clone(); hi = chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out[tag + "_ranks_agree"] = bool(lo.item() == hi.item())
+        ok &= out[tag + "_ranks_agree"]
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ok"] = bool(flag.item())
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    fs.comm_finalize()
+    dist.destroy_process_group()
+    return 0 if out["ok"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

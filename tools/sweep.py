@@ -1,9 +1,10 @@
-"""Sweep the CSR SpMM launch parameters on the C2 workload (one GPU).
+"""Sweep the CSR SpMM launch parameters on a bench workload (one GPU).
 
-    python tools/sweep.py [--workload c2] [--reps 5]
+    python tools/sweep.py [--workload c2] [--reps 5] [--combos "algo,tw,g,vec,slabs,rb;..."]
 
-Prints one line per (TW, G, VEC, slabs): ms per product, nnz*RHS/s, algorithmic GB/s.
-Used to pick the heuristic in kernels_csr.cu; results are copied into profiles/."""
+algo 1 = team-per-row kernel (tw, g, vec, slabs), algo 2 = staged row-block kernel (g, vec,
+slabs, rb = rows per CTA, 0 = automatic).  Prints one JSON line per setting: ms per product,
+nnz*RHS/s, algorithmic GB/s, max |diff| against the first setting."""
 import argparse
 import json
 import os
@@ -23,43 +24,49 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--R", type=int, default=0)
+    ap.add_argument("--vals", action="store_true")
+    ap.add_argument("--dist", type=int, default=-1)
+    ap.add_argument("--transpose", action="store_true", help="time the product with the cached transpose (A' X)")
     ap.add_argument("--combos", default="")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     nrow, ncol, nnz, R, dkind, seed = WORKLOADS[args.workload]
     if args.R:
         R = args.R
-    A = fs.DeviceMatrix.synth(seed, dkind, nnz, nrow, ncol)
-    X = torch.randn(ncol * R, dtype=torch.float64, device="cuda")
-    Y = torch.empty(nrow * R, dtype=torch.float64, device="cuda")
-    ref = None
+    if args.dist >= 0:
+        dkind = args.dist
+    A = fs.DeviceMatrix.synth(seed, dkind, nnz, nrow, ncol, with_vals=args.vals)
+    nin, nout = (nrow, ncol) if args.transpose else (ncol, nrow)
+    X = torch.randn(nin * R, dtype=torch.float64, device="cuda")
+    Y = torch.empty(nout * R, dtype=torch.float64, device="cuda")
+    run = (lambda: A.spmm_t(X, R, out=Y)) if args.transpose else (lambda: A.spmm(X, R, out=Y))
     if args.combos:
         combos = [tuple(int(v) for v in c.split(",")) for c in args.combos.split(";")]
     else:
-        combos = [(0, 0, 0, 0)]
+        combos = [(0, 0, 0, 0, 0, 0)]
         for vec in (4, 2, 1):
-            g = max(1, R // vec)
-            if g > 32:
+            if R % vec:
                 continue
+            g = 1
+            while g * vec < R and g < 32:
+                g *= 2
+            for rb in (0, 64, 256):
+                combos.append((2, 0, g, vec, 1, rb))
             for tw in (32, 16, 8):
                 if tw >= g:
-                    combos.append((tw, g, vec, 1))
-        for slabs in (2, 4):
-            for vec in (4, 2):
-                g = max(1, R // slabs // vec)
-                for tw in (32, 16):
-                    if tw >= g:
-                        combos.append((tw, g, vec, slabs))
+                    combos.append((1, tw, g, vec, 1, 0))
+    ref = None
     rows = []
-    for tw, g, vec, slabs in combos:
+    for algo, tw, g, vec, slabs, rb in combos:
+        fs.check(fs.lib().fsb_tune_csr_algo(algo, rb, 0))
         fs.check(fs.lib().fsb_tune_csr_spmm(tw, g, vec, slabs))
         for _ in range(2):
-            A.spmm(X, R, out=Y)
+            run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.reps):
-            A.spmm(X, R, out=Y)
+            run()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
@@ -68,7 +75,10 @@ def main():
             err = 0.0
         else:
             err = float((Y - ref).abs().max())
-        row = dict(tw=tw, g=g, vec=vec, slabs=slabs, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=alg_bytes(nrow, nnz, R) / ms / 1e6, maxdiff=err)
+        idx_bytes = 12 if args.vals else 4
+        ab = nnz * (idx_bytes + 8 * R) + 4 * (nout + 1) + 8 * nout * R if 8 * nin * R > 126e6 else \
+            nnz * idx_bytes + 4 * (nout + 1) + 8 * nout * R + 8 * nin * R
+        row = dict(algo=algo, tw=tw, g=g, vec=vec, slabs=slabs, rb=rb, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=ab / ms / 1e6, maxdiff=err)
         rows.append(row)
         print(json.dumps(row), flush=True)
     if args.out:
