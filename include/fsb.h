@@ -87,6 +87,14 @@ int fsb_matrix_info(fsb_matrix_t A, int* format, int* nrow, int* ncol, long* nnz
                     int* has_vals, int* nblocks);
 /* bytes of HBM held by the handle (structure + cached transposes) */
 long fsb_matrix_bytes(fsb_matrix_t A);
+/* row-blocked COO built on the device from a device COO; order 0 = COO order kept
+ * (new_bsbm), 1 = per-block Hilbert order (new_bsbm + sort_bsbm sparse.h:215-236),
+ * 2 = per-block row-major order (sort_bsbm_byrow sparse.h:238-256) */
+int fsb_blocked_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows,
+                             const int* d_cols, const double* d_vals, int block_size, int order);
+/* column-blocked binary CSR built on the device (new_cbcsr cbcsr.h:16-65) */
+int fsb_cbcsr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows,
+                           const int* d_cols, int colblocksize);
 /* copy the device CSR structure back (row_ptr nrow+1, cols nnz, vals nnz or NULL) */
 int fsb_csr_download(fsb_matrix_t A, int* row_ptr, int* cols, double* vals);
 /* a new handle holding rows [r0, r1) of a CSR handle (device-side slice,
@@ -227,9 +235,15 @@ void fsb_die(const char* where);
  * g = lanes per gathered dense row, vec = doubles per lane (1, 2 or 4), slabs =
  * column passes over the dense operand.  Used by tools/sweep.py and the tests. */
 int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs);
-/* algo: 0 automatic, 1 team-per-row kernel, 2 staged row-block kernel; rows_per_cta and
+/* algo: 0 automatic, 1 team-per-row kernel, 2 staged row-block kernel, 3 merge-path stream
+ * kernel (R = 1, 2, 4; what "automatic" picks for those widths); rows_per_cta and
  * cap_mult (staging capacity = cap_mult * mean entries per CTA) are 0 for automatic */
 int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult);
+
+/* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable
+ * CSR view of the same entries, built once on the device and cached in the handle;
+ * native = 1: the format's own kernels (kernels_blocked.cu, kernels_cbcsr.cu). */
+int fsb_tune_formats(int native);
 
 /* ------------------------------------------ synthetic inputs (bench) */
 /* Counter-based generator: entry j of the COO is a pure function of (seed, j),

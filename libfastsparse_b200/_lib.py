@@ -35,6 +35,8 @@ _SIGS = {
     "fsb_csr_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
     "fsb_csr_upload_coo": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
     "fsb_csr_from_coo_dev": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fsb_blocked_from_coo_dev": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fsb_cbcsr_from_coo_dev": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int]),
     "fsb_cbcsr_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, c_int_p, c_int_p]),
     "fsb_blocked_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp]),
     "fsb_matrix_free": (C.c_int, [handle]),
@@ -89,6 +91,7 @@ _SIGS = {
     "fsb_cache_clear": (None, []),
     "fsb_die": (None, [C.c_char_p]),
     "fsb_tune_csr_spmm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fsb_tune_formats": (C.c_int, [C.c_int]),
     "fsb_tune_csr_algo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fsb_synth_coo_dev": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsb_synth_coo_host": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),

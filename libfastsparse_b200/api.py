@@ -608,6 +608,20 @@ class DeviceMatrix:
             m.coo = (rows, cols, vals)
         return m
 
+    @classmethod
+    def blocked_from_coo_tensors(cls, nrow, ncol, rows, cols, vals, block_size, order=1):
+        """BlockedSBM/SDM built on the device; order 0 COO, 1 Hilbert (sort_bsbm), 2 by row (sort_bsbm_byrow)."""
+        h = handle()
+        check(lib().fsb_blocked_from_coo_dev(C.byref(h), nrow, ncol, rows.numel(), rows.data_ptr(), cols.data_ptr(),
+                                             vals.data_ptr() if vals is not None else None, block_size, order))
+        return cls(h)
+
+    @classmethod
+    def cbcsr_from_coo_tensors(cls, nrow, ncol, rows, cols, colblocksize):
+        h = handle()
+        check(lib().fsb_cbcsr_from_coo_dev(C.byref(h), nrow, ncol, rows.numel(), rows.data_ptr(), cols.data_ptr(), colblocksize))
+        return cls(h)
+
     def row_slice(self, r0, r1):
         h = handle()
         check(lib().fsb_csr_row_slice(C.byref(h), self.h, int(r0), int(r1)))

@@ -25,7 +25,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-fopenmp,-Wall,-Wno-unused-function",
               "--expt-relaxed-constexpr", "-I", INCLUDE]
 
-SOURCES = ["fsb_capi.cu", "kernels_csr.cu", "kernels_csr_staged.cu", "kernels_cbcsr.cu", "kernels_blocked.cu", "kernels_build.cu",
+SOURCES = ["fsb_capi.cu", "kernels_csr.cu", "kernels_csr_staged.cu", "kernels_csr_stream.cu", "kernels_cbcsr.cu", "kernels_blocked.cu", "kernels_build.cu",
            "kernels_dense.cu", "fsb_cg.cu", "fsb_comm.cu", "fsb_host.cpp", "fsb_dropin.cpp"]
 
 

@@ -105,12 +105,27 @@ int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out) {
   return FSB_OK;
 }
 
+int fsb_matrix_carry(fsb_matrix* A, size_t bytes, double** out) {
+  if (bytes > A->carry_cap) {
+    if (A->carry) cudaFree(A->carry);
+    A->carry = nullptr;
+    A->carry_cap = 0;
+    FSB_CUDA(cudaMalloc(&A->carry, bytes));
+    A->carry_cap = bytes;
+  }
+  *out = A->carry;
+  return FSB_OK;
+}
+
 static void free_arrays(fsb_matrix* A) {
   if (!A) return;
+  cudaFree(A->carry);
+  cudaFree(A->split);
   cudaFree(A->row_ptr); cudaFree(A->cols); cudaFree(A->vals);
   cudaFree(A->start_row); cudaFree(A->blk_off); cudaFree(A->b_rows); cudaFree(A->b_cols); cudaFree(A->b_vals);
   cudaFree(A->tmp);
   if (A->T) { free_arrays(A->T); delete A->T; }
+  if (A->view) { free_arrays(A->view); delete A->view; }
 }
 
 template <typename T>
@@ -237,7 +252,7 @@ int fsb_matrix_info(fsb_matrix_t A, int* format, int* nrow, int* ncol, long* nnz
 
 long fsb_matrix_bytes(fsb_matrix_t A) {
   if (!A) return 0;
-  return (long)(A->bytes + (A->T ? A->T->bytes : 0) + A->tmp_cap);
+  return (long)(A->bytes + (A->T ? A->T->bytes : 0) + (A->view ? A->view->bytes : 0) + A->tmp_cap + A->carry_cap);
 }
 
 int fsb_matrix_set_row_sharded(fsb_matrix_t A, int sharded) {
@@ -298,13 +313,21 @@ extern "C" int fsb_csr_row_slice(fsb_matrix_t* out, fsb_matrix_t A, int r0, int 
 }
 
 // ------------------------------------------------------------------ products
+static int g_native_formats = 0;
+
 static int spmm_any(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
-  switch (A->format) {
-    case FSB_FMT_CSR: return fsb_launch_csr_spmm(A, dY, dX, R, st);
-    case FSB_FMT_CBCSR: return fsb_launch_cbcsr_spmm(A, dY, dX, R, st);
-    case FSB_FMT_BLOCKED: return fsb_launch_blocked_spmm(A, dY, dX, R, st);
-  }
-  return fsb_set_error(FSB_EINVAL, "unknown matrix format %d", A->format);
+  if (A->format == FSB_FMT_CSR) return fsb_launch_csr_spmm(A, dY, dX, R, st);
+  if (A->format != FSB_FMT_CBCSR && A->format != FSB_FMT_BLOCKED) return fsb_set_error(FSB_EINVAL, "unknown matrix format %d", A->format);
+  if (g_native_formats)   // the format's own traversal (cell lists / row-class lists + shared-memory Y)
+    return A->format == FSB_FMT_CBCSR ? fsb_launch_cbcsr_spmm(A, dY, dX, R, st) : fsb_launch_blocked_spmm(A, dY, dX, R, st);
+  // default: the CSR kernels on the row-stable view of the same entries (built once, cached)
+  FSB_TRY(fsb_build_csr_view(A, st));
+  return fsb_launch_csr_spmm(A->view, dY, dX, R, st);
+}
+
+extern "C" int fsb_tune_formats(int native) {
+  g_native_formats = native != 0;
+  return FSB_OK;
 }
 
 // allreduce of a row shard's partial A'(...); no-op without a communicator

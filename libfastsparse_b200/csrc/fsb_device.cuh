@@ -27,6 +27,26 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p) {
   return v;
 }
 
+// L2 cache policy word for ld/st ...L2::cache_hint: 0 = normal, 1 = evict_last (keep the dense
+// operand resident), 2 = evict_first (streams that are touched once)
+__device__ __forceinline__ unsigned long long make_l2_policy(int kind) {
+  unsigned long long p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int ld_stream_s32_pol(const int* p, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double ld_stream_f64_pol(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // gather of VEC consecutive doubles of a dense operand row (read-only path).
 // VEC = 4 is one 256-bit LDG (sm_100+); the L2::evict_last form keeps the dense
 // operand resident in L2 against the streaming matrix/Y traffic.
@@ -35,10 +55,16 @@ template <> struct XLoad<1> {
   static __device__ __forceinline__ void ld(double* v, const double* p) {
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v[0]) : "l"(p));
   }
+  static __device__ __forceinline__ void ldp(double* v, const double* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v[0]) : "l"(p), "l"(pol));
+  }
 };
 template <> struct XLoad<2> {
   static __device__ __forceinline__ void ld(double* v, const double* p) {
     asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  }
+  static __device__ __forceinline__ void ldp(double* v, const double* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol));
   }
 };
 #ifndef FSB_X_EVICT_LAST
@@ -53,6 +79,10 @@ template <> struct XLoad<4> {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                  : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 #endif
+  }
+  static __device__ __forceinline__ void ldp(double* v, const double* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p), "l"(pol));
   }
 };
 

@@ -29,9 +29,16 @@ struct fsb_matrix {
   int max_block_rows = 0;
   // lazily built, cached transpose (CSR handles only)
   fsb_matrix* T = nullptr;
+  // lazily built CSR view of a blocked / column-blocked matrix (same entries, stable by row, so
+  // every row keeps its stored order); products default to the CSR kernels through it
+  fsb_matrix* view = nullptr;
   // library-owned scratch (A X intermediate of A'A, host staging)
   double* tmp = nullptr;
   size_t tmp_cap = 0;
+  double* carry = nullptr;    // per-tile carries of the merge-path stream kernel
+  size_t carry_cap = 0;
+  int* split = nullptr;       // cached merge-path tile boundaries (rows complete at each tile start)
+  int split_tile = 0;
   size_t bytes = 0;
   double avg_row_nnz = 0.0;
 };
@@ -67,9 +74,14 @@ static inline cudaStream_t fsb_pick_stream(void* s) {
 
 // ---- device scratch owned by a handle
 int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out);
+int fsb_matrix_carry(fsb_matrix* A, size_t bytes, double** out);
 
 // ---- kernels_csr.cu
-int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+// ---- kernels_csr_stream.cu (merge-path SpMV / narrow SpMM, R = 1, 2, 4)
+bool fsb_csr_stream_supports(int R);
+bool fsb_csr_stream_preferred(int R);
+int fsb_launch_csr_stream(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st);
 // tuning override for the sweep tool: TW, G, VEC, slabs (0 = heuristic)
 void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
@@ -86,6 +98,7 @@ int fsb_launch_blocked_spmm(const fsb_matrix* A, double* dY, const double* dX, i
 int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
                                const int* d_cols, const double* d_vals, cudaStream_t st);
 int fsb_build_transpose(fsb_matrix* A, cudaStream_t st);   // fills A->T
+int fsb_build_csr_view(fsb_matrix* A, cudaStream_t st);    // fills A->view (BLOCKED / CBCSR)
 int fsb_stable_perm_by_key(const int* d_keys, int nkeys, long n, int* d_perm, int* d_ptr, cudaStream_t st);
 #define FSB_BLOCKED_CLASSES 256
 int fsb_blocked_relayout(fsb_matrix* A, cudaStream_t st);  // bucket entries by row class; fills A->row_ptr

@@ -230,6 +230,54 @@ int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, co
   return coo_to_csr_dev(out, nrow, ncol, nnz, d_rows, d_cols, d_vals, st);
 }
 
+namespace {
+// row of every stored entry of a column-blocked CSR: cell = block*nrow + row (cbcsr.h:41)
+__global__ void expand_cell_rows_kernel(const int* __restrict__ cell_ptr, long long ncell, int nrow, long long nnz, int* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    long long lo = 0, hi = ncell;  // largest cell with cell_ptr[cell] <= i
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (cell_ptr[mid] <= i) lo = mid; else hi = mid;
+    }
+    out[i] = (int)(lo % nrow);
+  }
+}
+}  // namespace
+
+// CSR view of a blocked (row-blocked COO) or column-blocked matrix: the same entries stably
+// sorted by row.  Blocked: the class buckets are stable, so a row's entries keep their stored
+// (e.g. Hilbert) order.  Column-blocked: a row's cells follow each other in block order.
+int fsb_build_csr_view(fsb_matrix* A, cudaStream_t st) {
+  if (A->view) return FSB_OK;
+  fsb_matrix* V = new fsb_matrix();
+  int rc;
+  if (A->format == FSB_FMT_BLOCKED) {
+    rc = coo_to_csr_dev(V, A->nrow, A->ncol, A->nnz, A->b_rows, A->b_cols, A->b_vals, st);
+  } else if (A->format == FSB_FMT_CBCSR) {
+    int* rowid = nullptr;
+    cudaError_t e = cudaMalloc(&rowid, (size_t)std::max<long>(A->nnz, 1) * sizeof(int));
+    if (e != cudaSuccess) { delete V; return fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__); }
+    if (A->nnz > 0) {
+      expand_cell_rows_kernel<<<grid_for(A->nnz), 256, 0, st>>>(A->row_ptr, (long long)A->nblocks * A->nrow, A->nrow, A->nnz, rowid);
+      fsb_count_launch();
+    }
+    rc = coo_to_csr_dev(V, A->nrow, A->ncol, A->nnz, rowid, A->cols, nullptr, st);
+    cudaFree(rowid);
+  } else {
+    delete V;
+    return fsb_set_error(FSB_EINVAL, "csr view: blocked or column-blocked handle required");
+  }
+  if (rc != FSB_OK) {
+    cudaFree(V->row_ptr); cudaFree(V->cols); cudaFree(V->vals);
+    delete V;
+    return rc;
+  }
+  A->view = V;
+  return FSB_OK;
+}
+
 int fsb_build_transpose(fsb_matrix* A, cudaStream_t st) {
   if (A->T) return FSB_OK;
   if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "transpose: CSR handles only");
@@ -249,6 +297,172 @@ int fsb_build_transpose(fsb_matrix* A, cudaStream_t st) {
     return rc;
   }
   A->T = T;
+  return FSB_OK;
+}
+
+// ---------------------------------------------------------------- device-side builders for the blocked formats
+namespace {
+
+__device__ __forceinline__ long long dev_xy2d(int n, int x, int y) {   // hilbert.h:16-27 (+ rot 45-57), device twin
+  long long d = 0;
+  for (long long s = n / 2; s > 0; s /= 2) {
+    const int rx = (x & s) > 0, ry = (y & s) > 0;
+    d += s * s * (long long)((3 * rx) ^ ry);
+    if (!ry) {
+      if (rx) { x = (int)s - 1 - x; y = (int)s - 1 - y; }
+      const int t = x; x = y; y = t;
+    }
+  }
+  return d;
+}
+
+__device__ __forceinline__ int dev_ceil_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// composite 64-bit key: (block * 256 + row class) in the high bits, in-block order key below.
+// order 0: original position (stable COO order), 1: row_xy2d Hilbert key (sort_bsbm), 2: row*ncol+col
+__global__ void blocked_sortkey_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long nnz, int nrow,
+                                       int ncol, int block_size, int order, unsigned long long* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    const int r = rows[i], c = cols[i];
+    const int b = r / block_size;
+    const int r0 = b * block_size;
+    const int lr = r - r0;
+    unsigned long long low;
+    if (order == 1) {
+      const int n = dev_ceil_pow2(min(block_size, nrow - r0));
+      low = (unsigned long long)(dev_xy2d(n, c % n, lr) + (long long)n * n * (c / n));   // row_xy2d hilbert.h:60-65
+    } else if (order == 2) {
+      low = (unsigned long long)lr * (unsigned long long)ncol + (unsigned long long)c;
+    } else {
+      low = (unsigned long long)i;
+    }
+    const unsigned long long hi = (unsigned long long)b * FSB_BLOCKED_CLASSES + (unsigned long long)(lr & (FSB_BLOCKED_CLASSES - 1));
+    keys[i] = (hi << 40) | (low & ((1ull << 40) - 1));
+  }
+}
+
+__global__ void class_ptr_kernel(const unsigned long long* __restrict__ keys, long long n, int nkeys, int* __restrict__ ptr) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; j <= n; j += stride) {
+    const int lo = (j == 0) ? -1 : (int)(keys[j - 1] >> 40);
+    const int hi = (j == n) ? nkeys : (int)(keys[j] >> 40);
+    for (int q = lo + 1; q <= hi; ++q) ptr[q] = (int)j;
+  }
+}
+
+__global__ void cell_key_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long nnz, int nrow,
+                                int colblocksize, int* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) keys[i] = (cols[i] / colblocksize) * nrow + rows[i];
+}
+
+__global__ void block_meta_kernel(int* __restrict__ start_row, long* __restrict__ blk_off, const int* __restrict__ cls_ptr,
+                                  int nblocks, int nrow, int block_size) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nblocks) return;
+  start_row[b] = b < nblocks ? b * block_size : nrow;
+  blk_off[b] = cls_ptr[(long long)b * FSB_BLOCKED_CLASSES];
+}
+
+}  // namespace
+
+// Row-blocked COO built on the device from a device COO: equivalent to
+// new_bsbm (sparse.h:175-213) followed by nothing (order 0), sort_bsbm (order 1, sparse.h:215-236)
+// or sort_bsbm_byrow (order 2, sparse.h:238-256), directly in the kernel's class-bucketed layout.
+extern "C" int fsb_blocked_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows, const int* d_cols,
+                                        const double* d_vals, int block_size, int order) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow <= 0 || ncol <= 0 || nnz < 0 || block_size <= 0 || order < 0 || order > 2 || (nnz > 0 && (!d_rows || !d_cols)))
+    return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: bad arguments");
+  const int nblocks = (nrow + block_size - 1) / block_size;
+  const long nkeys_l = (long)nblocks * FSB_BLOCKED_CLASSES;
+  if (nkeys_l >= (1L << 24)) return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: too many row blocks (%d) for the 24-bit class key", nblocks);
+  if (order == 1) {
+    int n = 1; while (n < std::min(block_size, nrow)) n <<= 1;
+    if ((double)n * ncol >= (double)(1ull << 40)) return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: Hilbert key exceeds 40 bits");
+  }
+  cudaStream_t st = fsb_default_stream();
+  fsb_matrix* A = new fsb_matrix();
+  A->format = FSB_FMT_BLOCKED; A->nrow = nrow; A->ncol = ncol; A->nnz = nnz; A->nblocks = nblocks; A->has_vals = d_vals != nullptr;
+  A->max_block_rows = std::min(block_size, nrow);
+  A->avg_row_nnz = (double)nnz / nrow;
+  const int nkeys = (int)nkeys_l;
+  const size_t n1 = (size_t)std::max<long>(nnz, 1);
+  unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+  int *iota = nullptr, *perm = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cudaError_t e = cudaMalloc(&A->row_ptr, ((size_t)nkeys + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&A->start_row, ((size_t)nblocks + 1) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&A->blk_off, ((size_t)nblocks + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&A->b_rows, n1 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&A->b_cols, n1 * 4);
+  if (e == cudaSuccess && d_vals) e = cudaMalloc(&A->b_vals, n1 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&keys, n1 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&keys_sorted, n1 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&iota, n1 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&perm, n1 * 4);
+  if (e == cudaSuccess && nnz > 0) {
+    blocked_sortkey_kernel<<<grid_for(nnz), 256, 0, st>>>(d_rows, d_cols, nnz, nrow, ncol, block_size, order, keys);
+    iota_kernel<<<grid_for(nnz), 256, 0, st>>>(iota, nnz);
+    fsb_count_launch(2);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, iota, perm, (long long)nnz, 0, 64, st);
+    e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, iota, perm, (long long)nnz, 0, 64, st);
+    fsb_count_launch(9);
+    if (e == cudaSuccess) {
+      class_ptr_kernel<<<grid_for(nnz + 1), 256, 0, st>>>(keys_sorted, nnz, nkeys, A->row_ptr);
+      gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(A->b_rows, d_rows, perm, nnz);
+      gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(A->b_cols, d_cols, perm, nnz);
+      if (d_vals) gather_f64_kernel<<<grid_for(nnz), 256, 0, st>>>(A->b_vals, d_vals, perm, nnz);
+      fsb_count_launch(d_vals ? 4 : 3);
+    }
+  } else if (e == cudaSuccess) {
+    e = cudaMemsetAsync(A->row_ptr, 0, ((size_t)nkeys + 1) * 4, st);
+  }
+  if (e == cudaSuccess) {
+    block_meta_kernel<<<(nblocks + 256) / 256, 256, 0, st>>>(A->start_row, A->blk_off, A->row_ptr, nblocks, nrow, block_size);
+    fsb_count_launch();
+    e = cudaStreamSynchronize(st);
+  }
+  cudaFree(keys); cudaFree(keys_sorted); cudaFree(iota); cudaFree(perm); cudaFree(tmp);
+  if (e != cudaSuccess) {
+    const int rc = fsb_cuda_error(e, "fsb_blocked_from_coo_dev", __FILE__, __LINE__);
+    fsb_matrix_free(A);
+    return rc;
+  }
+  A->bytes = ((size_t)nkeys + 1) * 4 + ((size_t)nblocks + 1) * 12 + n1 * (d_vals ? 16 : 8);
+  *out = A;
+  return FSB_OK;
+}
+
+// Column-blocked binary CSR built on the device (new_cbcsr cbcsr.h:16-65): stable sort by cell.
+extern "C" int fsb_cbcsr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows, const int* d_cols,
+                                      int colblocksize) {
+  FSB_TRY(fsb_require_device());
+  if (!out || nrow <= 0 || ncol <= 0 || nnz < 0 || colblocksize <= 0 || (nnz > 0 && (!d_rows || !d_cols)))
+    return fsb_set_error(FSB_EINVAL, "fsb_cbcsr_from_coo_dev: bad arguments");
+  const int nblocks = (ncol + colblocksize - 1) / colblocksize;
+  const long ncell = (long)nblocks * nrow;
+  if (ncell >= INT32_MAX) return fsb_set_error(FSB_EINVAL, "fsb_cbcsr_from_coo_dev: nblocks*nrow exceeds the int32 cell range (cbcsr.h:41)");
+  cudaStream_t st = fsb_default_stream();
+  int* keys = nullptr;
+  FSB_CUDA(cudaMalloc(&keys, (size_t)std::max<long>(nnz, 1) * 4));
+  if (nnz > 0) {
+    cell_key_kernel<<<grid_for(nnz), 256, 0, st>>>(d_rows, d_cols, nnz, nrow, colblocksize, keys);
+    fsb_count_launch();
+  }
+  fsb_matrix* A = new fsb_matrix();
+  int rc = coo_to_csr_dev(A, (int)ncell, ncol, nnz, keys, d_cols, nullptr, st);
+  cudaFree(keys);
+  if (rc != FSB_OK) { fsb_matrix_free(A); return rc; }
+  A->format = FSB_FMT_CBCSR; A->nrow = nrow; A->ncol = ncol; A->nblocks = nblocks; A->colblocksize = colblocksize;
+  A->avg_row_nnz = (double)nnz / nrow;
+  *out = A;
   return FSB_OK;
 }
 

@@ -166,7 +166,8 @@ __global__ void scale_copy_kernel(double* __restrict__ Y, const double* __restri
 }
 
 int g_tw = 0, g_g = 0, g_vec = 0, g_slabs = 0;
-int g_algo = 0;   // 0 = automatic, 1 = team-per-row kernel (this file), 2 = staged row-block kernel
+int g_algo = 0;   // 0 = automatic, 1 = team-per-row kernel (this file), 2 = staged row-block kernel,
+                  // 3 = merge-path stream kernel where it applies (R = 1, 2, 4), staged otherwise
 
 inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 inline int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p <<= 1; return p; }
@@ -247,7 +248,7 @@ void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs) {
 }
 
 extern "C" int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult) {
-  if (algo < 0 || algo > 2 || rows_per_cta < 0 || cap_mult < 0) return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_algo: bad argument");
+  if (algo < 0 || algo > 3 || rows_per_cta < 0 || cap_mult < 0) return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_algo: bad argument");
   g_algo = algo;
   fsb_csr_staged_set_tuning(rows_per_cta, cap_mult);
   return FSB_OK;
@@ -261,21 +262,34 @@ extern "C" int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs) {
   return FSB_OK;
 }
 
-int fsb_launch_csr_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
   if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
   if (A->nrow == 0) return FSB_OK;
+  // one to four right-hand sides: matrix-streaming bound -> merge-path stream kernel
+  if ((g_algo == 3 && fsb_csr_stream_supports(R)) || (g_algo == 0 && fsb_csr_stream_preferred(R))) return fsb_launch_csr_stream(A, dY, dX, R, st);
   const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY;
-  int vec = (R % 4 == 0 && al % 32 == 0) ? 4 : (R % 2 == 0 && al % 16 == 0) ? 2 : 1;
+  const int algo = (g_algo == 1) ? 1 : 2;
+  // 128-bit gathers (16 lanes per 256-byte X row) beat the 256-bit form on B200 for the staged
+  // kernel at R = 32 (profiles/r1b_sweep_c2_staged_vs_team.json); the 256-bit form is kept
+  // for wide operands where it halves the number of column passes
+  // narrow operands: at least two lanes per row (R = 2 -> 2 x 1, R = 4 -> 2 x 2) measured
+  // 1.3-2x faster than one wide lane (profiles/r1c_small_R.md)
+  int vec = (R % 4 == 0 && al % 32 == 0 && (algo == 1 || R > 64)) ? 4 : (R % 2 == 0 && R >= 4 && al % 16 == 0) ? 2 : 1;
   if (g_vec && (R % g_vec == 0) && (al % (8 * g_vec) == 0)) vec = g_vec;
   // columns handled per pass: at most 32 lanes * vec; optional slab split keeps the
   // per-pass footprint of the dense operand inside L2
   int per_pass = std::min(R, 32 * vec);
-  if (g_slabs > 1 && R % (g_slabs * vec) == 0) per_pass = std::min(per_pass, R / g_slabs);
+  // dense operand larger than L2: two column passes of >= 128 B per gather halve the per-pass
+  // footprint (more L2 hits) at the price of streaming the indices twice: ~5 % faster on C2
+  // (profiles/r1c_c2_l2policy_slabs.md)
+  // (measured: -5 % on uniform columns but +25 % on power-law columns and on A' products whose
+  // operand is far larger than L2, so it stays an opt-in: fsb_tune_csr_spmm(..., slabs))
+  const int slabs = g_slabs;
+  if (slabs > 1 && per_pass % (slabs * vec) == 0) per_pass = per_pass / slabs;
   int g = pow2_ceil((per_pass + vec - 1) / vec);
   if (g_g && g_g >= g && g_g <= 32) g = g_g;
   int tw = pick_tw(g, A->avg_row_nnz);
   if (g_tw && g_tw >= g && g_tw <= 32) tw = g_tw;
-  const int algo = g_algo ? g_algo : 2;
   for (int col0 = 0; col0 < R; col0 += per_pass) {
     const int ncols = std::min(per_pass, R - col0);
     if (algo == 2) {

@@ -35,7 +35,8 @@ constexpr int kLongRow = 2048;   // rows at least this long are split across the
 
 template <int G, int VEC, bool VALS, bool FROM_SMEM>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
-                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok) {
+                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok,
+                                         unsigned long long xpol) {
   constexpr int U = FSB_STAGED_U;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
@@ -46,7 +47,7 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
       if (idx < e && col_ok) {
         const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
         if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
-        XLoad<VEC>::ld(xr[u], xbase + (long long)c * R);
+        XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
       } else {
         if (VALS) vv[u] = 0.0;
 #pragma unroll
@@ -64,7 +65,7 @@ template <int G, int VEC, bool VALS>
 __global__ void __launch_bounds__(kThreads)
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                       int R, int col0, int ncols, int RB, int CAP) {
+                       int R, int col0, int ncols, int RB, int CAP, int l2mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -81,6 +82,9 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
   const int nr = min(RB, nrow - r0);
   const bool col_ok = l * VEC < ncols;
   const double* xbase = X + col0 + l * VEC;
+  // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
+  const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
+  const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
 
   for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptr + r0 + i);
   __syncthreads();
@@ -89,15 +93,15 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
 
   if (total <= CAP) {
     for (int i = tid; i < total; i += kThreads) {
-      s_cols[i] = ld_stream_s32(cols + base + i);
-      if (VALS) s_vals[i] = ld_stream_f64(vals + base + i);
+      s_cols[i] = ld_stream_s32_pol(cols + base + i, spol);
+      if (VALS) s_vals[i] = ld_stream_f64_pol(vals + base + i, spol);
     }
     __syncthreads();
     for (int r = team; r < nr; r += NT) {
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok);
+      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok, xpol);
       if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
     }
     return;
@@ -114,7 +118,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, col_ok);
+      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, col_ok, xpol);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -132,13 +136,13 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, col_ok);
+      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, col_ok, xpol);
       if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
     }
   }
 }
 
-int g_rb = 0, g_cap_mult = 0;
+int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 
 inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -149,7 +153,7 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
-  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP);
+  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode);
   return FSB_OK;
 }
 
@@ -170,7 +174,11 @@ int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, 
 
 }  // namespace
 
-void fsb_csr_staged_set_tuning(int rb, int cap_mult) { g_rb = rb; g_cap_mult = cap_mult; }
+void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
+  g_rb = rb;
+  g_cap_mult = cap_mult % 100;           // hundreds digit of cap_mult selects the L2 policy experiment:
+  g_l2mode = (cap_mult / 100) == 1 ? 0 : 1;   // 1xx = no cache hints, otherwise X evict_last / stream evict_first
+}
 
 // one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,

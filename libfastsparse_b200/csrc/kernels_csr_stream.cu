@@ -1,0 +1,222 @@
+// kernels_csr_stream.cu -- CSR SpMV / narrow SpMM (R = 1, 2, 4), merge-path "stream" kernel.
+//
+// Same products as bcsr_A_mul_B / _B2 / _B4 (csr.h:149-202) and csr_A_mul_B (csr.h:425-438),
+// and -- through the cached transpose -- At_mul_B / sdm_At_mul_B (sparse.h:68-75,
+// dsparse.h:54-62).  With one or a few right-hand sides the product is bound by STREAMING the
+// matrix (4 or 12 bytes per entry); the dense operand is small and L2-resident.  Row-wise
+// kernels cannot stream well: short rows leave lanes idle, long rows (10^5 entries in the
+// transpose of a power-law matrix) serialise a CTA.  Here the work is split by ENTRIES, not
+// rows (merge-path, Merrill & Garland): CTA b takes items [bT, (b+1)T) of the merged list
+// (row ends, entries); its two end points are found by binary search in row_ptr.
+//   1. all 256 threads load the CTA's run of cols/vals with coalesced loads and write the
+//      products x[col]*val into shared memory: gather parallelism is independent of rows;
+//   2. one thread per row that ENDS in the tile sums its segment in stored order and stores
+//      Y[row];
+//   3. the piece of the row that continues into the next tile goes to a carry slot; a tiny
+//      fix-up kernel adds the carries in tile order.  Deterministic, no atomics, perfectly
+//      balanced for any row-length distribution, empty rows included.
+#include <algorithm>
+
+#include "fsb_device.cuh"
+#include "fsb_internal.h"
+
+using namespace fsbdev;
+
+namespace {
+
+constexpr int kThreads = 256;
+// merged items (row ends + entries) per CTA: 16 KB of products in shared memory for every width
+template <int RT> struct Tile { static constexpr int n = 2048 / RT; };
+
+// merge-path split: first i such that row_end[i] > d - i - 1, i.e. rows [0,i) are complete
+// once d items of the merged (row ends, entries) sequence are consumed
+__device__ __forceinline__ int merge_search(const int* __restrict__ row_ptr, int nrow, long long nnz, long long d) {
+  long long lo = d > nnz ? d - nnz : 0;
+  long long hi = d < nrow ? d : nrow;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)__ldg(row_ptr + mid + 1) <= d - mid - 1) lo = mid + 1; else hi = mid;
+  }
+  return (int)lo;
+}
+
+// the tile boundaries depend only on the matrix: computed once per (matrix, tile size) and cached
+__global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, int tile, int ntiles, int* __restrict__ split) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > ntiles) return;
+  const long long total = (long long)nrow + nnz;
+  const long long d = min((long long)b * tile, total);
+  split[b] = merge_search(row_ptr, nrow, nnz, d);
+}
+
+template <int RT, bool VALS>
+__global__ void __launch_bounds__(kThreads)
+csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                  const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                  const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {
+  constexpr int kTile = Tile<RT>::n;
+  __shared__ int s_end[kTile + 1];
+  __shared__ double s_p[kTile * RT];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long total = (long long)nrow + nnz;
+  const long long d0 = (long long)blockIdx.x * kTile;
+  const long long d1 = min(d0 + kTile, total);
+  const int i0 = __ldg(split + blockIdx.x), i1 = __ldg(split + blockIdx.x + 1);
+  const long long j0 = d0 - i0, j1 = d1 - i1;
+  const int ndone = i1 - i0;            // rows whose end falls in this tile
+  const int nn = (int)(j1 - j0);        // entries in this tile
+  const int nend = ndone + (i1 < nrow ? 1 : 0);
+  for (int k = tid; k < nend; k += kThreads) s_end[k] = __ldg(row_ptr + i0 + 1 + k);
+  {
+    // all of this thread's entries are loaded before any gather is issued, and all gathers
+    // before any product is stored: PER independent loads in flight per thread in each phase
+    constexpr int PER = kTile / kThreads;
+    int c[PER];
+    double v[PER];
+    double xv[PER][RT];
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      c[p] = 0;
+      v[p] = 1.0;
+      if (t < nn) {
+        c[p] = ld_stream_s32(cols + j0 + t);
+        if (VALS) v[p] = ld_stream_f64(vals + j0 + t);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+#pragma unroll
+      for (int k = 0; k < RT; ++k) xv[p][k] = (t < nn) ? __ldg(X + (long long)c[p] * RT + k) : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      if (t < nn) {
+#pragma unroll
+        for (int k = 0; k < RT; ++k) s_p[t * RT + k] = VALS ? xv[p][k] * v[p] : xv[p][k];
+      }
+    }
+  }
+  __syncthreads();
+  if (ndone * 8 >= nn) {
+    // short rows (< 8 entries on average): one thread per row, stored order
+    for (int k = tid; k < ndone; k += kThreads) {
+      const int s = (k == 0) ? 0 : (int)(s_end[k - 1] - j0);
+      const int e = (int)(s_end[k] - j0);
+      double acc[RT];
+#pragma unroll
+      for (int q = 0; q < RT; ++q) acc[q] = 0.0;
+      for (int t = s; t < e; ++t)
+#pragma unroll
+        for (int q = 0; q < RT; ++q) acc[q] += s_p[t * RT + q];
+#pragma unroll
+      for (int q = 0; q < RT; ++q) Y[(long long)(i0 + k) * RT + q] = acc[q];
+    }
+  } else {
+    // longer rows: one warp per row, lanes stride over the segment, fixed shuffle tree
+    for (int k = warp; k < ndone; k += kThreads / 32) {
+      const int s = (k == 0) ? 0 : (int)(s_end[k - 1] - j0);
+      const int e = (int)(s_end[k] - j0);
+      double acc[RT];
+#pragma unroll
+      for (int q = 0; q < RT; ++q) acc[q] = 0.0;
+      for (int t = s + lane; t < e; t += 32)
+#pragma unroll
+        for (int q = 0; q < RT; ++q) acc[q] += s_p[t * RT + q];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int q = 0; q < RT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < RT; ++q) Y[(long long)(i0 + k) * RT + q] = acc[q];
+      }
+    }
+  }
+  // the row that continues past this tile: its piece here becomes a carry
+  if (tid < 32) {
+    const int s = (ndone == 0) ? 0 : (int)(s_end[ndone - 1] - j0);
+    double acc[RT];
+#pragma unroll
+    for (int q = 0; q < RT; ++q) acc[q] = 0.0;
+    const bool has = (i1 < nrow) && (s < nn);
+    if (has) {
+      for (int t = s + tid; t < nn; t += 32)
+#pragma unroll
+        for (int q = 0; q < RT; ++q) acc[q] += s_p[t * RT + q];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int q = 0; q < RT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+    if (tid == 0) {
+      carry_row[blockIdx.x] = has ? i1 : -1;
+#pragma unroll
+      for (int q = 0; q < RT; ++q) carry_val[(long long)blockIdx.x * RT + q] = acc[q];
+    }
+  }
+}
+
+// add the carried pieces to their rows, run by run, in tile order (deterministic)
+template <int RT>
+__global__ void csr_stream_fixup_kernel(int ntiles, const int* __restrict__ carry_row, const double* __restrict__ carry_val,
+                                        double* __restrict__ Y) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= ntiles) return;
+  const int row = carry_row[b];
+  if (row < 0 || (b > 0 && carry_row[b - 1] == row)) return;
+  double acc[RT];
+#pragma unroll
+  for (int q = 0; q < RT; ++q) acc[q] = 0.0;
+  for (int t = b; t < ntiles && carry_row[t] == row; ++t)
+#pragma unroll
+    for (int q = 0; q < RT; ++q) acc[q] += carry_val[(long long)t * RT + q];
+#pragma unroll
+  for (int q = 0; q < RT; ++q) Y[(long long)row * RT + q] += acc[q];
+}
+
+template <int RT, bool VALS>
+int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
+  constexpr int kTile = Tile<RT>::n;
+  const long long total = (long long)A->nrow + A->nnz;
+  const int ntiles = (int)((total + kTile - 1) / kTile);
+  if (ntiles == 0) return FSB_OK;
+  double* scratch = nullptr;
+  FSB_TRY(fsb_matrix_carry(A, (size_t)ntiles * (RT * sizeof(double) + sizeof(int)) + 16, &scratch));
+  double* carry_val = scratch;
+  int* carry_row = reinterpret_cast<int*>(scratch + (size_t)ntiles * RT);
+  if (A->split_tile != kTile) {   // tile boundaries: once per matrix and tile size
+    if (A->split) cudaFree(A->split);
+    A->split = nullptr;
+    A->split_tile = 0;
+    FSB_CUDA(cudaMalloc(&A->split, ((size_t)ntiles + 1) * sizeof(int)));
+    merge_splits_kernel<<<(ntiles + 256) / 256, 256, 0, st>>>(A->nrow, A->nnz, A->row_ptr, kTile, ntiles, A->split);
+    FSB_KERNEL_CHECK();
+    A->split_tile = kTile;
+  }
+  csr_stream_kernel<RT, VALS><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
+  FSB_KERNEL_CHECK();
+  csr_stream_fixup_kernel<RT><<<(ntiles + 255) / 256, 256, 0, st>>>(ntiles, carry_row, carry_val, dY);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+}  // namespace
+
+// R = 2 and 4 are implemented (and tested) but the staged row kernel is faster there
+// (profiles/r1c_small_R.md): the automatic choice uses the stream kernel for R = 1 only.
+bool fsb_csr_stream_supports(int R) { return R == 1 || R == 2 || R == 4; }
+bool fsb_csr_stream_preferred(int R) { return R == 1; }
+
+int fsb_launch_csr_stream(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+  if (A->nrow == 0) return FSB_OK;
+  switch (R) {
+    case 1: return A->has_vals ? launch<1, true>(A, dY, dX, st) : launch<1, false>(A, dY, dX, st);
+    case 2: return A->has_vals ? launch<2, true>(A, dY, dX, st) : launch<2, false>(A, dY, dX, st);
+    case 4: return A->has_vals ? launch<4, true>(A, dY, dX, st) : launch<4, false>(A, dY, dX, st);
+  }
+  return fsb_set_error(FSB_EINVAL, "stream kernel: R must be 1, 2 or 4 (got %d)", R);
+}

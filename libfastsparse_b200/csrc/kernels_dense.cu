@@ -15,42 +15,56 @@
 namespace {
 
 constexpr int kGramCtas = 148 * 2;
-constexpr int kTile = 32;  // rows staged per step
+constexpr int kTile = 64;  // rows staged per step
 
-// partial[cta][Ra*Rb] = sum over this CTA's rows of Xa[i][a] * Xb[i][b]
+// partial[cta][R*R] = sum over this CTA's rows of Xa[i][a] * Xb[i][b].
+// Register-tiled mini GEMM: thread (kgroup, ta, tb) accumulates a 4x4 block of the (padded)
+// 32x32 result over every fourth row of the staged tile; the four row groups are combined
+// through shared memory at the end.  Fixed order => bit-reproducible.
 __global__ void __launch_bounds__(256)
 gram_partial_kernel(double* __restrict__ partial, const double* __restrict__ Xa, const double* __restrict__ Xb,
                     long long n, int R) {
-  __shared__ double sa[kTile][33];
-  __shared__ double sb[kTile][33];
-  // thread owns entries e = tid + 256*q of the R x R result (q < 4)
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  __shared__ __align__(16) double sm[2 * kTile * 32];
+  double (*sa)[32] = reinterpret_cast<double (*)[32]>(sm);
+  double (*sb)[32] = reinterpret_cast<double (*)[32]>(sm + kTile * 32);
   const int tid = threadIdx.x;
-  const int RR = R * R;
+  const int kg = tid >> 6, u = tid & 63;
+  const int a0 = (u >> 3) * 4, b0 = (u & 7) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   for (long long base = (long long)blockIdx.x * kTile; base < n; base += (long long)gridDim.x * kTile) {
     const int rows = (int)min((long long)kTile, n - base);
-    for (int e = tid; e < rows * R; e += 256) {
-      const int r = e / R, c = e - r * R;
-      sa[r][c] = Xa[(base + r) * R + c];
-      sb[r][c] = Xb[(base + r) * R + c];
+    for (int e = tid; e < kTile * 32; e += 256) {
+      const int r = e >> 5, c = e & 31;
+      const bool ok = r < rows && c < R;
+      sa[r][c] = ok ? Xa[(base + r) * R + c] : 0.0;
+      sb[r][c] = ok ? Xb[(base + r) * R + c] : 0.0;
     }
     __syncthreads();
+    for (int r = kg; r < kTile; r += 4) {
+      const double2 av0 = *reinterpret_cast<const double2*>(&sa[r][a0]), av1 = *reinterpret_cast<const double2*>(&sa[r][a0 + 2]);
+      const double2 bv0 = *reinterpret_cast<const double2*>(&sb[r][b0]), bv1 = *reinterpret_cast<const double2*>(&sb[r][b0 + 2]);
+      const double av[4] = {av0.x, av0.y, av1.x, av1.y};
+      const double bv[4] = {bv0.x, bv0.y, bv1.x, bv1.y};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int e = tid + 256 * q;
-      if (e < RR) {
-        const int a = e / R, b = e - a * R;
-        double s = acc[q];
-        for (int r = 0; r < rows; ++r) s = fma(sa[r][a], sb[r][b], s);
-        acc[q] = s;
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
+  // combine the four row groups: sm viewed as [4][1024]
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int e = tid + 256 * q;
-    if (e < RR) partial[(size_t)blockIdx.x * RR + e] = acc[q];
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm[kg * 1024 + (a0 + i) * 32 + (b0 + j)] = acc[i][j];
+  __syncthreads();
+  for (int e = tid; e < 1024; e += 256) {
+    const int a = e >> 5, b = e & 31;
+    if (a < R && b < R) partial[(size_t)blockIdx.x * R * R + a * R + b] = (sm[e] + sm[1024 + e]) + (sm[2048 + e] + sm[3072 + e]);
   }
 }
 
@@ -90,40 +104,61 @@ __global__ void cg_norms_kernel(double* __restrict__ norm, double* __restrict__ 
   inorm[k] = 1.0 / nv;
 }
 
-// Out1[i,:] += In1[i,:] * M ; Out2[i,:] -= In2[i,:] * M      (cg.h:148-154)
-// or (mode 1) Out1[i,:] = Add[i,:] + Out1[i,:] * M            (cg.h:165-170)
-// M is R x R, M[k][j] = coefficient of input column k in output column j.
+// O[i,:] (op)= I[i,:] * M for a tall row-major [n][R] operand and an R x R matrix M
+// (M[k][j] = coefficient of input column k in output column j):
+//   MODE 0: O += I M      (X += P alpha,      cg.h:148-151)
+//   MODE 1: O -= I M      (R -= KP alpha,     cg.h:152-153)
+//   MODE 2: O  = Add + I M, I may alias O     (P = R + P psi, cg.h:165-170)
+// 128 rows per tile staged in shared memory; each thread owns a 4 (rows) x 4 (cols) block.
+constexpr int kMixRows = 128;
 template <int MODE>
 __global__ void __launch_bounds__(256)
-cg_rowmix_kernel(double* __restrict__ O1, const double* __restrict__ I1, double* __restrict__ O2,
-                 const double* __restrict__ I2, const double* __restrict__ M, long long n, int R) {
-  __shared__ double sm[32][33];
-  __shared__ double s1[8][33];
-  __shared__ double s2[8][33];
+cg_rowmix_kernel(double* O, const double* I, const double* __restrict__ Add,
+                 const double* __restrict__ M, long long n, int R) {
+  __shared__ __align__(16) double smat[32][32];
+  __shared__ double sin[kMixRows][33];
   const int tid = threadIdx.x;
-  for (int e = tid; e < R * R; e += 256) sm[e / R][e % R] = M[e];
-  const int r = tid >> 5, j = tid & 31;
-  for (long long base = (long long)blockIdx.x * 8; base < n; base += (long long)gridDim.x * 8) {
-    const long long row = base + r;
-    const bool ok = row < n && j < R;
+  for (int e = tid; e < 1024; e += 256) {
+    const int k = e >> 5, j = e & 31;
+    smat[k][j] = (k < R && j < R) ? M[k * R + j] : 0.0;
+  }
+  const int tj = tid & 7, ti = tid >> 3;
+  const int j0 = tj * 4;
+  for (long long base = (long long)blockIdx.x * kMixRows; base < n; base += (long long)gridDim.x * kMixRows) {
+    const int rows = (int)min((long long)kMixRows, n - base);
     __syncthreads();
-    if (ok) {
-      s1[r][j] = (MODE == 0) ? I1[row * R + j] : O1[row * R + j];
-      if (MODE == 0) s2[r][j] = I2[row * R + j];
+    for (int e = tid; e < rows * R; e += 256) {
+      const int r = e / R, c = e - r * R;
+      sin[r][c] = I[(base + r) * R + c];
     }
     __syncthreads();
-    if (ok) {
-      double a = 0.0, b = 0.0;
-      for (int k = 0; k < R; ++k) {
-        const double m = sm[k][j];
-        a = fma(s1[r][k], m, a);
-        if (MODE == 0) b = fma(s2[r][k], m, b);
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k = 0; k < R; ++k) {
+      const double2 m0 = *reinterpret_cast<const double2*>(&smat[k][j0]), m1 = *reinterpret_cast<const double2*>(&smat[k][j0 + 2]);
+      const double mv[4] = {m0.x, m0.y, m1.x, m1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double x = sin[ti + 32 * i][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(x, mv[j], acc[i][j]);
       }
-      if (MODE == 0) {
-        O1[row * R + j] += a;
-        O2[row * R + j] -= b;
-      } else {
-        O1[row * R + j] = I1[row * R + j] + a;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ti + 32 * i;
+      if (r >= rows) continue;
+      const long long off = (base + r) * R;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = j0 + j;
+        if (c >= R) continue;
+        if (MODE == 0) O[off + c] += acc[i][j];
+        else if (MODE == 1) O[off + c] -= acc[i][j];
+        else O[off + c] = Add[off + c] + acc[i][j];
       }
     }
   }
@@ -242,16 +277,18 @@ int fsb_dense_cg_init(double* dX, double* dRm, double* dP, const double* dB, con
 
 int fsb_dense_cg_update_xr(double* dX, const double* dP, double* dRm, const double* dKP, const double* dAlpha, long n, int R, cudaStream_t st) {
   if (n <= 0) return FSB_OK;
-  const int ctas = (int)std::min<long long>((n + 7) / 8, 148LL * 8);
-  cg_rowmix_kernel<0><<<ctas, 256, 0, st>>>(dX, dP, dRm, dKP, dAlpha, n, R);
+  const int ctas = (int)std::min<long long>((n + kMixRows - 1) / kMixRows, 148LL * 4);
+  cg_rowmix_kernel<0><<<ctas, 256, 0, st>>>(dX, dP, nullptr, dAlpha, n, R);
+  FSB_KERNEL_CHECK();
+  cg_rowmix_kernel<1><<<ctas, 256, 0, st>>>(dRm, dKP, nullptr, dAlpha, n, R);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }
 
 int fsb_dense_cg_update_p(double* dP, const double* dRm, const double* dPsi, long n, int R, cudaStream_t st) {
   if (n <= 0) return FSB_OK;
-  const int ctas = (int)std::min<long long>((n + 7) / 8, 148LL * 8);
-  cg_rowmix_kernel<1><<<ctas, 256, 0, st>>>(dP, dRm, nullptr, nullptr, dPsi, n, R);
+  const int ctas = (int)std::min<long long>((n + kMixRows - 1) / kMixRows, 148LL * 4);
+  cg_rowmix_kernel<2><<<ctas, 256, 0, st>>>(dP, dP, dRm, dPsi, n, R);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }
@@ -294,7 +331,7 @@ extern "C" int fsb_gram_dev(double* G_host, const double* dXa, const double* dXb
 }
 
 namespace {
-__global__ void diff_kernel(double* __restrict__ d, const double* __restrict__ x, const double* __restrict__ y, long long n) {
+__global__ void diff_kernel(double* d, const double* x, const double* __restrict__ y, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) d[i] = x[i] - y[i];

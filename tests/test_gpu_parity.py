@@ -138,7 +138,7 @@ def _random_case(rng, nrow, ncol, nnz, long_row=0):
     return rows, cols, rng.random(nnz)
 
 
-@pytest.fixture(params=[1, 2], ids=["team-kernel", "staged-kernel"])
+@pytest.fixture(params=[1, 2, 3], ids=["team-kernel", "staged-kernel", "stream-kernel"])
 def csr_algo(request):
     """Run a test once per CSR SpMM kernel (fsb_tune_csr_algo), then restore the automatic choice."""
     fs.check(fs.lib().fsb_tune_csr_algo(request.param, 0, 0))
@@ -182,9 +182,17 @@ def test_csr_products_ragged(R, csr_algo):
         assert_close(Z, oracle.csr_mul(ncol, trp, tcc, tvv, Xt, R), sct, what=f"csr^T R={R} vals={v is not None}")
 
 
+@pytest.fixture(params=[0, 1], ids=["csr-view", "native-format-kernel"])
+def format_mode(request):
+    """Blocked / column-blocked products: default CSR view vs the format's own kernel (fsb_tune_formats)."""
+    fs.check(fs.lib().fsb_tune_formats(request.param))
+    yield request.param
+    fs.check(fs.lib().fsb_tune_formats(0))
+
+
 @pytest.mark.parametrize("R", [1, 2, 3, 8, 32, 40])
 @pytest.mark.parametrize("bs", [1, 7, 64, 500, 5000])
-def test_blocked_products_ragged(R, bs):
+def test_blocked_products_ragged(R, bs, format_mode):
     rng = np.random.default_rng(R * 1000 + bs)
     nrow, ncol, nnz = 2000, 333, 15000
     rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=600)
@@ -202,7 +210,7 @@ def test_blocked_products_ragged(R, bs):
 
 @pytest.mark.parametrize("R", [1, 4, 32])
 @pytest.mark.parametrize("colblock", [1, 5, 64, 1000])
-def test_cbcsr_products_ragged(R, colblock):
+def test_cbcsr_products_ragged(R, colblock, format_mode):
     rng = np.random.default_rng(R * 7 + colblock)
     nrow, ncol, nnz = 1500, 640, 20000
     rows, cols, _ = _random_case(rng, nrow, ncol, nnz, long_row=3000)
@@ -378,3 +386,37 @@ def test_full_size_c2_properties():
     Z = M.ata(X, R)
     lhs = (X.reshape(F, R) * Z.reshape(F, R)).sum(0); rhs = (Y.reshape(N, R) ** 2).sum(0)
     assert torch.allclose(lhs, rhs, rtol=1e-10)
+
+
+# ------------------------------------------------------------------ device-side builders of the blocked formats
+@pytest.mark.parametrize("bs", [64, 512])
+@pytest.mark.parametrize("with_vals", [False, True])
+def test_device_blocked_builder_matches_host_sort_bsbm(bs, with_vals):
+    import torch
+    nrow, ncol, nnz, R = 3000, 5000, 40000, 8
+    rows, cols, vals = fs.synth_coo_host(77, 1, nnz, nrow, ncol, with_vals=True)
+    keep = np.unique(rows.astype(np.int64) * ncol + cols, return_index=True)[1]      # unique coordinates: order is unique
+    rows, cols, vals = rows[keep], cols[keep], (vals[keep] if with_vals else None)
+    A = fs.SparseBinaryMatrix(nrow, ncol, rows, cols) if vals is None else fs.SparseDoubleMatrix(nrow, ncol, rows, cols, vals)
+    Bl = fs.new_bsbm(A, bs); fs.sort_bsbm(Bl)
+    X = torch.randn(ncol * R, dtype=torch.float64, device="cuda")
+    Yh = fs.DeviceMatrix.of(Bl).spmm(X, R)
+    tr, tc = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+    tv = torch.from_numpy(vals).cuda() if vals is not None else None
+    for order in (0, 1, 2):
+        D = fs.DeviceMatrix.blocked_from_coo_tensors(nrow, ncol, tr, tc, tv, bs, order=order)
+        Yd = D.spmm(X, R)
+        if order == 1:
+            assert torch.equal(Yd, Yh), "device Hilbert order differs from host sort_bsbm order"
+        assert torch.allclose(Yd, Yh, rtol=1e-13, atol=1e-12)
+
+
+def test_device_cbcsr_builder_matches_host():
+    import torch
+    nrow, ncol, nnz, R = 2500, 3000, 50000, 4
+    rows, cols, _ = fs.synth_coo_host(78, 1, nnz, nrow, ncol)
+    Cb = fs.new_cbcsr(256, nnz, nrow, ncol, rows, cols)
+    X = torch.randn(ncol * R, dtype=torch.float64, device="cuda")
+    Yh = fs.DeviceMatrix.of(Cb).spmm(X, R)
+    D = fs.DeviceMatrix.cbcsr_from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), 256)
+    assert D.nblocks == Cb.nblocks and torch.equal(D.spmm(X, R), Yh)

@@ -1,0 +1,158 @@
+"""Measure every BASELINE.json config on one GPU (C2-C5) with the kernel's roofline and,
+where cheap, the reference CPU function on a bounded sample.  One JSON line per measurement.
+
+    python tools/bench_all.py [--small] [--out gpurun_out/bench_all.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import libfastsparse_b200 as fs  # noqa: E402
+from bench import measured_peaks  # noqa: E402
+
+L2 = 126e6
+
+
+def timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def spmm_bytes(nnz, nout, nin, R, idx_bytes, extra=0):
+    """matrix arrays, output and row_ptr once; dense input per gather when it exceeds L2, else once."""
+    dense = nnz * 8 * R if 8 * nin * R > L2 else 8 * nin * R
+    return nnz * idx_bytes + dense + 4 * (nout + 1) + 8 * nout * R + extra
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    N, F, NNZ = (1_000_000, 100_000, 20_000_000) if args.small else (10_000_000, 1_000_000, 200_000_000)
+    peak, _ = measured_peaks()
+    out = open(args.out, "w") if args.out else None
+
+    def emit(**kw):
+        kw["frac_of_measured_peak"] = kw["alg_gbs"] / peak if "alg_gbs" in kw else None
+        line = json.dumps(kw)
+        print(line, flush=True)
+        if out:
+            out.write(line + "\n"); out.flush()
+
+    want = set(args.only.split(",")) if args.only else None
+    on = lambda k: want is None or k in want
+
+    # ---------------- C3: double CSR SpMV + At_mul_B
+    if on("c3"):
+        A = fs.DeviceMatrix.synth(0x5EED0003, 0, NNZ, N, F, with_vals=True)
+        x = (torch.sin(7.0 * torch.arange(F, device="cuda", dtype=torch.float64) + 0.3) / 10).contiguous()
+        y = torch.empty(N, dtype=torch.float64, device="cuda")
+        ms = timed(lambda: A.spmm(x, 1, out=y), args.reps)
+        ab = spmm_bytes(NNZ, N, F, 1, 12)
+        emit(config="C3 double CSR SpMV (csr_A_mul_B)", ms=ms, nnz_per_s=NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        z = torch.empty(F, dtype=torch.float64, device="cuda")
+        A.spmm_t(y, 1, out=z)
+        ms = timed(lambda: A.spmm_t(y, 1, out=z), args.reps)
+        ab = spmm_bytes(NNZ, F, N, 1, 12)
+        emit(config="C3 double CSR At_mul_B (stored transpose, sdm_At_mul_B)", ms=ms, nnz_per_s=NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        for mode in (0, 1):
+            ms = timed(lambda: A.ata(x, 1, mode=mode, out=z), args.reps)
+            ab = (2 * 12 * NNZ + 4 * (N + F + 2) + 16 * N + 16 * F) if mode == 0 else (12 * NNZ + 4 * (N + 1) + 16 * F)
+            emit(config=f"C3 double CSR A'(A x) mode {mode} ({'two gather passes' if mode == 0 else 'fused red.add scatter'})", ms=ms,
+                 nnz_visits_per_s=2 * NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        # binary SpMV on the same structure (bcsr_A_mul_B) and fused A'A (parallel_bcsr_AA_mul_B)
+        del A
+        B = fs.DeviceMatrix.synth(0x5EED0003, 0, NNZ, N, F)
+        ms = timed(lambda: B.spmm(x, 1, out=y), args.reps)
+        ab = spmm_bytes(NNZ, N, F, 1, 4)
+        emit(config="binary CSR SpMV (bcsr_A_mul_B)", ms=ms, nnz_per_s=NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        for mode in (0, 1):
+            ms = timed(lambda: B.ata(x, 1, mode=mode, out=z), args.reps)
+            ab = (2 * 4 * NNZ + 4 * (N + F + 2) + 16 * N + 16 * F) if mode == 0 else (8 * NNZ + 4 * (N + 1) + 16 * F)
+            emit(config=f"binary CSR A'(A x) mode {mode} (bcsr_AA_mul_B / parallel_bcsr_AA_mul_B)", ms=ms,
+                 nnz_visits_per_s=2 * NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        for R in (2, 4, 8, 16):
+            X = torch.randn(F * R, dtype=torch.float64, device="cuda"); Y = torch.empty(N * R, dtype=torch.float64, device="cuda")
+            ms = timed(lambda: B.spmm(X, R, out=Y), args.reps)
+            ab = spmm_bytes(NNZ, N, F, R, 4)
+            emit(config=f"binary CSR SpMM R={R} (bcsr_A_mul_B{R if R <= 8 else 'n'})", ms=ms, nnz_rhs_per_s=NNZ * R / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+            del X, Y
+        del B
+
+    # ---------------- C4: power-law columns, R = 32, blocked (Hilbert) and column-blocked formats
+    if on("c4"):
+        R = 32
+        M = fs.DeviceMatrix.synth(0x5EED0004, 1, NNZ, N, F, keep_coo=True)
+        rows, cols, _ = M.coo
+        X = torch.randn(F * R, dtype=torch.float64, device="cuda"); Y = torch.empty(N * R, dtype=torch.float64, device="cuda")
+        ms = timed(lambda: M.spmm(X, R, out=Y), args.reps)
+        ab = spmm_bytes(NNZ, N, F, R, 4)
+        emit(config="C4 power-law cols, binary CSR SpMM R=32", ms=ms, nnz_rhs_per_s=NNZ * R / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        Yref = Y.clone()
+        for bs in (512, 256):
+            t0 = time.perf_counter()
+            Bk = fs.DeviceMatrix.blocked_from_coo_tensors(N, F, rows, cols, None, bs, order=1)
+            torch.cuda.synchronize(); build_s = time.perf_counter() - t0
+            ms = timed(lambda: Bk.spmm(X, R, out=Y), args.reps)
+            ab = NNZ * (8 + 8 * R) + 8 * N * R
+            emit(config=f"C4 BlockedSBM bs={bs} Hilbert-sorted (bsbm_A_mul_Bn R=32)", ms=ms, nnz_rhs_per_s=NNZ * R / ms * 1e3, alg_bytes=ab,
+                 alg_gbs=ab / ms / 1e6, maxdiff_vs_csr=float((Y - Yref).abs().max()), device_build_s=build_s)
+            del Bk
+        t0 = time.perf_counter()
+        Cb = fs.DeviceMatrix.cbcsr_from_coo_tensors(N, F, rows, cols, 65536)
+        torch.cuda.synchronize(); build_s = time.perf_counter() - t0
+        ms = timed(lambda: Cb.spmm(X, R, out=Y), args.reps)
+        ab = NNZ * (4 + 8 * R) + 4 * (Cb.nblocks * N + 1) + 8 * N * R
+        emit(config="C4 ColBinaryCSR colblock=65536 (cbcsr_A_mul_Bn R=32)", ms=ms, nnz_rhs_per_s=NNZ * R / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6,
+             maxdiff_vs_csr=float((Y - Yref).abs().max()), device_build_s=build_s, nblocks=Cb.nblocks)
+        x = torch.randn(F, dtype=torch.float64, device="cuda"); y = torch.empty(N, dtype=torch.float64, device="cuda")
+        ms = timed(lambda: Cb.spmm(x, 1, out=y), args.reps)
+        ab = 4 * NNZ + 4 * (Cb.nblocks * N + 1) + 8 * N + 8 * F
+        emit(config="C4 ColBinaryCSR colblock=65536 (cbcsr_A_mul_B R=1)", ms=ms, nnz_per_s=NNZ / ms * 1e3, alg_bytes=ab, alg_gbs=ab / ms / 1e6)
+        del Cb, M, X, Y, Yref, rows, cols
+
+    # ---------------- C5: block CG (lambda I + A'A) X = B, R = 32, on the C2 matrix
+    if on("c5"):
+        R = 32
+        M = fs.DeviceMatrix.synth(0x5EED0002, 0, NNZ, N, F)
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        Nn = torch.randn(N * R, dtype=torch.float64, device="cuda", generator=g)
+        E = torch.randn(F * R, dtype=torch.float64, device="cuda", generator=g)
+        Bm = M.spmm_t(Nn, R) + (15.0 ** 0.5) * E          # B = A'N + sqrt(lambda) E   (bench_a_mul_b.c:334-347)
+        del Nn, E
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        Xs, it = M.cg(Bm, R, lam=15.0, tol=1e-6)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        res = (M.ata(Xs, R, lam=15.0) - Bm).reshape(F, R).norm(dim=0) / Bm.reshape(F, R).norm(dim=0)
+        per_it = dt / max(it + 1, 1)
+        ab = (NNZ * (4 + 8 * R) + 4 * (N + 1) + 8 * N * R) + (NNZ * (4 + 8 * R) + 4 * (F + 1) + 8 * F * R) + 11 * 8 * F * R
+        emit(config="C5 block CG R=32 lambda=15 tol=1e-6 (bsbm_cgn on CSR + cached transpose)", iterations=it, seconds=dt, ms_per_iteration=per_it * 1e3,
+             nnz_rhs_per_s=2 * NNZ * R / per_it, alg_bytes=ab, alg_gbs=ab / per_it / 1e9, max_rel_residual=float(res.max()))
+        ms = timed(lambda: M.ata(Xs, R, lam=15.0), 5)
+        emit(config="C5 operator (lambda I + A'A) X, R=32, two gather passes", ms=ms, nnz_rhs_per_s=2 * NNZ * R / ms * 1e3)
+    if out:
+        out.close()
+
+
+if __name__ == "__main__":
+    main()
