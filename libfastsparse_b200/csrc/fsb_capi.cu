@@ -21,6 +21,7 @@ int g_device = -1;
 cudaStream_t g_stream = nullptr;
 cudaStream_t g_copy_stream = nullptr;
 std::atomic<long> g_launches{0};
+int g_native_formats = 0;   // fsb_tune_formats: 1 = the blocked formats' own kernels, 0 = CSR view
 }  // namespace
 
 int fsb_set_error(int code, const char* fmt, ...) {
@@ -313,8 +314,6 @@ extern "C" int fsb_csr_row_slice(fsb_matrix_t* out, fsb_matrix_t A, int r0, int 
 }
 
 // ------------------------------------------------------------------ products
-static int g_native_formats = 0;
-
 static int spmm_any(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
   if (A->format == FSB_FMT_CSR) return fsb_launch_csr_spmm(A, dY, dX, R, st);
   if (A->format != FSB_FMT_CBCSR && A->format != FSB_FMT_BLOCKED) return fsb_set_error(FSB_EINVAL, "unknown matrix format %d", A->format);
@@ -431,6 +430,33 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
   const size_t bx = (size_t)A->ncol * R * 8, by = (size_t)A->nrow * R * 8;
   FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
   if (bx) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, bx, cudaMemcpyHostToDevice, g_stream));
+  // Large results are dominated by the D2H copy of Y over PCIe.  Row chunks are independent, so
+  // the product is issued chunk by chunk and chunk i is copied out (second stream) while chunk
+  // i+1 is computed: the kernel time disappears behind the copy.
+  fsb_matrix* C = A;
+  if (A->format != FSB_FMT_CSR && !g_native_formats) {
+    FSB_TRY(fsb_build_csr_view(A, g_stream));
+    C = A->view;
+  }
+  const int kChunks = 8;
+  if (C->format == FSB_FMT_CSR && R >= 2 && by >= ((size_t)64 << 20) && C->nrow >= 1024 * kChunks) {
+    const int per = (C->nrow + kChunks - 1) / kChunks;
+    for (int c = 0; c < kChunks; ++c) {
+      const int r0 = c * per, r1 = std::min(C->nrow, r0 + per);
+      if (r0 >= r1) break;
+      fsb_matrix part;                 // rows [r0, r1): row_ptr values stay absolute, so cols/vals are shared
+      part.format = FSB_FMT_CSR; part.nrow = r1 - r0; part.ncol = C->ncol; part.nnz = C->nnz; part.has_vals = C->has_vals;
+      part.row_ptr = C->row_ptr + r0; part.cols = C->cols; part.vals = C->vals; part.avg_row_nnz = C->avg_row_nnz;
+      double* dYc = g_stage.dY + (size_t)r0 * R;
+      FSB_TRY(fsb_launch_csr_spmm(&part, dYc, g_stage.dX, R, g_stream));
+      FSB_CUDA(cudaEventRecord(g_stage.ev[c & 1], g_stream));
+      FSB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_stage.ev[c & 1], 0));
+      FSB_CUDA(cudaMemcpyAsync(Y + (size_t)r0 * R, dYc, (size_t)(r1 - r0) * R * 8, cudaMemcpyDeviceToHost, g_copy_stream));
+    }
+    FSB_CUDA(cudaStreamSynchronize(g_copy_stream));
+    FSB_CUDA(cudaStreamSynchronize(g_stream));
+    return FSB_OK;
+  }
   FSB_TRY(spmm_any(A, g_stage.dY, g_stage.dX, R, g_stream));
   if (by) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, by, cudaMemcpyDeviceToHost, g_stream));
   FSB_CUDA(cudaStreamSynchronize(g_stream));

@@ -16,6 +16,7 @@
 //      fix-up kernel adds the carries in tile order.  Deterministic, no atomics, perfectly
 //      balanced for any row-length distribution, empty rows included.
 #include <algorithm>
+#include <type_traits>
 
 #include "fsb_device.cuh"
 #include "fsb_internal.h"
@@ -101,41 +102,38 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
     }
   }
   __syncthreads();
-  if (ndone * 8 >= nn) {
-    // short rows (< 8 entries on average): one thread per row, stored order
-    for (int k = tid; k < ndone; k += kThreads) {
+  // rows ending in this tile: GL lanes per row chosen from the tile's mean row length
+  // (1 lane for short rows -- a shuffle tree per 20-entry row costs more than the sum itself --
+  // 8 lanes up to ~128 entries, a full warp beyond); lanes stride over the segment and are
+  // combined by a fixed shuffle tree, so the result does not depend on scheduling
+  auto reduce_rows = [&](auto gl_tag) {
+    constexpr int GL = decltype(gl_tag)::value;
+    const int grp = tid / GL, gl = tid % GL;
+    for (int k = grp; k < ndone; k += kThreads / GL) {
       const int s = (k == 0) ? 0 : (int)(s_end[k - 1] - j0);
       const int e = (int)(s_end[k] - j0);
       double acc[RT];
 #pragma unroll
       for (int q = 0; q < RT; ++q) acc[q] = 0.0;
-      for (int t = s; t < e; ++t)
+      for (int t = s + gl; t < e; t += GL)
 #pragma unroll
         for (int q = 0; q < RT; ++q) acc[q] += s_p[t * RT + q];
+      if (GL > 1) {
+        const unsigned mask = GL == 32 ? 0xffffffffu : (((1u << GL) - 1u) << (lane - gl));
 #pragma unroll
-      for (int q = 0; q < RT; ++q) Y[(long long)(i0 + k) * RT + q] = acc[q];
-    }
-  } else {
-    // longer rows: one warp per row, lanes stride over the segment, fixed shuffle tree
-    for (int k = warp; k < ndone; k += kThreads / 32) {
-      const int s = (k == 0) ? 0 : (int)(s_end[k - 1] - j0);
-      const int e = (int)(s_end[k] - j0);
-      double acc[RT];
+        for (int off = GL / 2; off > 0; off >>= 1)
 #pragma unroll
-      for (int q = 0; q < RT; ++q) acc[q] = 0.0;
-      for (int t = s + lane; t < e; t += 32)
-#pragma unroll
-        for (int q = 0; q < RT; ++q) acc[q] += s_p[t * RT + q];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-        for (int q = 0; q < RT; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
-      if (lane == 0) {
+          for (int q = 0; q < RT; ++q) acc[q] += __shfl_xor_sync(mask, acc[q], off, GL);
+      }
+      if (gl == 0) {
 #pragma unroll
         for (int q = 0; q < RT; ++q) Y[(long long)(i0 + k) * RT + q] = acc[q];
       }
     }
-  }
+  };
+  if (nn <= 24 * ndone) reduce_rows(std::integral_constant<int, 1>{});
+  else if (nn <= 128 * ndone) reduce_rows(std::integral_constant<int, 8>{});
+  else reduce_rows(std::integral_constant<int, 32>{});
   // the row that continues past this tile: its piece here becomes a carry
   if (tid < 32) {
     const int s = (ndone == 0) ? 0 : (int)(s_end[ndone - 1] - j0);

@@ -40,7 +40,11 @@ def main():
         tag = f"{'dbl' if with_vals else 'bin'}_R{R}"
         # A x: no collective, the shard's slab is bit-identical to the full product's rows
         Y = full.spmm(X, R)
-        out[tag + "_Ax_slab_equal"] = bool(torch.equal(shard.spmm(X, R), Y[r0 * R: r1 * R]))
+        Ys = shard.spmm(X, R)
+        # row-local kernels (R >= 2) give bit-identical slabs; the merge-path SpMV (R = 1) associates
+        # rows that straddle tile boundaries differently in the shard, so compare to rounding there
+        out[tag + "_Ax_slab_equal"] = bool(torch.equal(Ys, Y[r0 * R: r1 * R])) if R >= 2 else \
+            bool(torch.allclose(Ys, Y[r0 * R: r1 * R], rtol=1e-13, atol=1e-12))
         # A' x: allreduce of partials inside the library
         Z = full.spmm_t(Xt, R)
         Zs = shard.spmm_t(Xt[r0 * R: r1 * R].contiguous(), R)
