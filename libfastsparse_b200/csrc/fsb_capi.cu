@@ -447,8 +447,10 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
       fsb_matrix part;                 // rows [r0, r1): row_ptr values stay absolute, so cols/vals are shared
       part.format = FSB_FMT_CSR; part.nrow = r1 - r0; part.ncol = C->ncol; part.nnz = C->nnz; part.has_vals = C->has_vals;
       part.row_ptr = C->row_ptr + r0; part.cols = C->cols; part.vals = C->vals; part.avg_row_nnz = C->avg_row_nnz;
+      part.tuned_R = C->tuned_R; part.tuned_passes = C->tuned_passes;   // share the handle's autotune decision
       double* dYc = g_stage.dY + (size_t)r0 * R;
       FSB_TRY(fsb_launch_csr_spmm(&part, dYc, g_stage.dX, R, g_stream));
+      C->tuned_R = part.tuned_R; C->tuned_passes = part.tuned_passes;
       FSB_CUDA(cudaEventRecord(g_stage.ev[c & 1], g_stream));
       FSB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_stage.ev[c & 1], 0));
       FSB_CUDA(cudaMemcpyAsync(Y + (size_t)r0 * R, dYc, (size_t)(r1 - r0) * R * 8, cudaMemcpyDeviceToHost, g_copy_stream));

@@ -39,6 +39,9 @@ struct fsb_matrix {
   size_t carry_cap = 0;
   int* split = nullptr;       // cached merge-path tile boundaries (rows complete at each tile start)
   int split_tile = 0;
+  int max_row_nnz = -1;       // longest row (lazy; SpMV kernel choice)
+  int tuned_R = 0;            // column-pass autotune of the staged SpMM (see fsb_launch_csr_spmm)
+  int tuned_passes = 1;
   size_t bytes = 0;
   double avg_row_nnz = 0.0;
 };

@@ -235,7 +235,7 @@ bool dispatch_fused(int tw, int g, const fsb_matrix* A, double* dY, const double
 int pick_tw(int g, double avg_nnz) {
   // wide gathers (g >= 8): two sub-groups per ~20-entry row measured best on B200
   // (profiles/r1_sweep_c2.md); narrow gathers want more lanes on the row's index stream
-  const double per_sub = g >= 8 ? 8.0 : 2.0;
+  const double per_sub = g >= 8 ? 8.0 : 4.0;
   int want = pow2_floor(std::max(1, (int)(avg_nnz / per_sub)));
   int ns = std::min(want, 32 / g);
   return g * std::max(ns, 1);
@@ -262,34 +262,45 @@ extern "C" int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs) {
   return FSB_OK;
 }
 
-int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
-  if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
-  if (A->nrow == 0) return FSB_OK;
-  // one to four right-hand sides: matrix-streaming bound -> merge-path stream kernel
-  if ((g_algo == 3 && fsb_csr_stream_supports(R)) || (g_algo == 0 && fsb_csr_stream_preferred(R))) return fsb_launch_csr_stream(A, dY, dX, R, st);
-  const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY;
-  const int algo = (g_algo == 1) ? 1 : 2;
-  // 128-bit gathers (16 lanes per 256-byte X row) beat the 256-bit form on B200 for the staged
-  // kernel at R = 32 (profiles/r1b_sweep_c2_staged_vs_team.json); the 256-bit form is kept
-  // for wide operands where it halves the number of column passes
-  // narrow operands: at least two lanes per row (R = 2 -> 2 x 1, R = 4 -> 2 x 2) measured
-  // 1.3-2x faster than one wide lane (profiles/r1c_small_R.md)
-  int vec = (R % 4 == 0 && al % 32 == 0 && (algo == 1 || R > 64)) ? 4 : (R % 2 == 0 && R >= 4 && al % 16 == 0) ? 2 : 1;
-  if (g_vec && (R % g_vec == 0) && (al % (8 * g_vec) == 0)) vec = g_vec;
-  // columns handled per pass: at most 32 lanes * vec; optional slab split keeps the
-  // per-pass footprint of the dense operand inside L2
-  int per_pass = std::min(R, 32 * vec);
-  // dense operand larger than L2: two column passes of >= 128 B per gather halve the per-pass
-  // footprint (more L2 hits) at the price of streaming the indices twice: ~5 % faster on C2
-  // (profiles/r1c_c2_l2policy_slabs.md)
-  // (measured: -5 % on uniform columns but +25 % on power-law columns and on A' products whose
-  // operand is far larger than L2, so it stays an opt-in: fsb_tune_csr_spmm(..., slabs))
-  const int slabs = g_slabs;
-  if (slabs > 1 && per_pass % (slabs * vec) == 0) per_pass = per_pass / slabs;
+namespace {
+
+__global__ void max_row_kernel(const int* __restrict__ row_ptr, int nrow, int* __restrict__ out) {
+  int m = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrow; r += gridDim.x * blockDim.x)
+    m = max(m, __ldg(row_ptr + r + 1) - __ldg(row_ptr + r));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// longest row of the matrix, computed once per handle (drives the SpMV kernel choice)
+int max_row_nnz(fsb_matrix* A, cudaStream_t st, int* out) {
+  if (A->max_row_nnz < 0) {
+    int* d = nullptr;
+    FSB_CUDA(cudaMalloc(&d, sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(int), st);
+    if (e == cudaSuccess) {
+      max_row_kernel<<<148 * 4, 256, 0, st>>>(A->row_ptr, A->nrow, d);
+      fsb_count_launch();
+      int h = 0;
+      e = cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) A->max_row_nnz = h;
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return fsb_cuda_error(e, "max_row_nnz", __FILE__, __LINE__);
+  }
+  *out = A->max_row_nnz;
+  return FSB_OK;
+}
+
+// one product with a fixed configuration (column passes of per_pass columns)
+int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int vec, int per_pass, int g_override,
+               int tw_override, cudaStream_t st) {
   int g = pow2_ceil((per_pass + vec - 1) / vec);
-  if (g_g && g_g >= g && g_g <= 32) g = g_g;
+  if (g_override >= g && g_override <= 32) g = g_override;
   int tw = pick_tw(g, A->avg_row_nnz);
-  if (g_tw && g_tw >= g && g_tw <= 32) tw = g_tw;
+  if (tw_override >= g && tw_override <= 32) tw = tw_override;
   for (int col0 = 0; col0 < R; col0 += per_pass) {
     const int ncols = std::min(per_pass, R - col0);
     if (algo == 2) {
@@ -301,6 +312,69 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
     FSB_KERNEL_CHECK();
   }
   return FSB_OK;
+}
+
+}  // namespace
+
+int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+  if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
+  if (A->nrow == 0) return FSB_OK;
+  const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY;
+  // ---- one right-hand side: the product is bound by the L1 sector-gather rate of x (200 M random
+  // 8-byte gathers), so the kernel with the least overhead wins when rows are regular: the
+  // team-per-row kernel.  Skewed matrices (a row far longer than the mean, e.g. transposes of
+  // power-law matrices) go to the entry-balanced merge-path stream kernel (230 ms -> 1.9 ms).
+  if (R == 1 && (g_algo == 0 || g_algo == 3)) {
+    bool stream = g_algo == 3;
+    if (!stream) {
+      int mx = 0;
+      FSB_TRY(max_row_nnz(A, st, &mx));
+      stream = mx > std::max(4096.0, 64.0 * A->avg_row_nnz);
+    }
+    if (stream) return fsb_launch_csr_stream(A, dY, dX, R, st);
+    return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st);
+  }
+  if (g_algo == 3 && fsb_csr_stream_supports(R)) return fsb_launch_csr_stream(A, dY, dX, R, st);
+  const int algo = (g_algo == 1) ? 1 : 2;
+  // 128-bit gathers (16 lanes per 256-byte X row) beat the 256-bit form on B200 for the staged
+  // kernel at R = 32 (profiles/r1b_sweep_c2_staged_vs_team.json); the 256-bit form is kept for
+  // wide operands where it halves the number of column passes.  Narrow operands: at least two
+  // lanes per row (R = 2 -> 2 x 1, R = 4 -> 2 x 2) measured 1.3-2x faster than one wide lane.
+  int vec = (R % 4 == 0 && al % 32 == 0 && (algo == 1 || R > 64)) ? 4 : (R % 2 == 0 && R >= 4 && al % 16 == 0) ? 2 : 1;
+  if (g_vec && (R % g_vec == 0) && (al % (8 * g_vec) == 0)) vec = g_vec;
+  int per_pass = std::min(R, 32 * vec);
+  if (g_slabs >= 1) {   // explicit choice (tools/sweep.py)
+    if (g_slabs > 1 && per_pass % (g_slabs * vec) == 0) per_pass /= g_slabs;
+    return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+  }
+  // ---- automatic: when the dense operand does not fit in L2, two column passes of >= 128 B per
+  // gather halve the per-pass footprint (more L2 hits) at the price of streaming the indices
+  // twice.  That is 15 % faster on uniform columns and 25 % slower on power-law columns (whose hot
+  // columns hit L2 anyway) -- not predictable from the shape, so the first product on a handle
+  // times both (results are identical: each column's sum is untouched) and the handle remembers.
+  const bool candidate = algo == 2 && (double)A->ncol * R * 8.0 > 126e6 && per_pass % (2 * vec) == 0 &&
+                         per_pass / 2 * 8 >= 128 && A->nnz >= (1 << 22);
+  if (!candidate) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+  if (A->tuned_R != R) {
+    cudaEvent_t ev[3];
+    for (auto& e : ev) FSB_CUDA(cudaEventCreate(&e));
+    int rc = FSB_OK;
+    cudaEventRecord(ev[0], st);
+    rc = run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+    cudaEventRecord(ev[1], st);
+    if (rc == FSB_OK) rc = run_config(A, dY, dX, R, algo, vec, per_pass / 2, g_g, g_tw, st);
+    cudaEventRecord(ev[2], st);
+    float t1 = 0.f, t2 = 0.f;
+    if (rc == FSB_OK && cudaEventSynchronize(ev[2]) == cudaSuccess) {
+      cudaEventElapsedTime(&t1, ev[0], ev[1]);
+      cudaEventElapsedTime(&t2, ev[1], ev[2]);
+      A->tuned_R = R;
+      A->tuned_passes = (t2 < 0.97f * t1) ? 2 : 1;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+  }
+  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st);
 }
 
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st) {
