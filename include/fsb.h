@@ -149,6 +149,12 @@ int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const double* dB, in
 int fsb_gram_dev(double* G_host, const double* dXa, const double* dXb, long n, int R, void* stream);
 /* same with HOST operands (the drop-in linalg.h path): copies Xa, Xb in, reduces on the GPU */
 int fsb_gram_host(double* G, const double* Xa, const double* Xb, long n, int R);
+/* Tall-skinny row mix with an R x R coefficient matrix dM (device, row-major), R <= 32; the
+ * vector updates of bsbm_cg / bsbm_cg2 (cg.h:60-63,70-73,148-154,165-170):
+ *   mode 0: O += I M;   mode 1: O -= I M and, when G_host != NULL, G_host = O'O of the updated O;
+ *   mode 2: O = Add + I M (I may alias O).   All operands [n][R] device pointers. */
+int fsb_rowmix_dev(int mode, double* dO, const double* dI, const double* dAdd, const double* dM,
+                   double* G_host, long n, int R, void* stream);
 /* *out = sqrt(sum (x[i]-y[i])^2) on the GPU, host operands.  Replaces dist linalg.h:6-13. */
 int fsb_dist_host(double* out, const double* x, const double* y, long n);
 

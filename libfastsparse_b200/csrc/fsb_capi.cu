@@ -314,14 +314,18 @@ extern "C" int fsb_csr_row_slice(fsb_matrix_t* out, fsb_matrix_t A, int r0, int 
 }
 
 // ------------------------------------------------------------------ products
-static int spmm_any(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
-  if (A->format == FSB_FMT_CSR) return fsb_launch_csr_spmm(A, dY, dX, R, st);
+// Y = A X (+ lambda Z, Z shaped like Y, when dZ != nullptr)
+static int spmm_any(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0) {
+  if (A->format == FSB_FMT_CSR) return fsb_launch_csr_spmm(A, dY, dX, R, st, dZ, lambda);
   if (A->format != FSB_FMT_CBCSR && A->format != FSB_FMT_BLOCKED) return fsb_set_error(FSB_EINVAL, "unknown matrix format %d", A->format);
-  if (g_native_formats)   // the format's own traversal (cell lists / row-class lists + shared-memory Y)
-    return A->format == FSB_FMT_CBCSR ? fsb_launch_cbcsr_spmm(A, dY, dX, R, st) : fsb_launch_blocked_spmm(A, dY, dX, R, st);
+  if (g_native_formats) {  // the format's own traversal (cell lists / row-class lists + shared-memory Y)
+    FSB_TRY(A->format == FSB_FMT_CBCSR ? fsb_launch_cbcsr_spmm(A, dY, dX, R, st) : fsb_launch_blocked_spmm(A, dY, dX, R, st));
+    if (dZ) FSB_TRY(fsb_dense_axpy_lambda(dY, dZ, lambda, (long)A->nrow * R, st));
+    return FSB_OK;
+  }
   // default: the CSR kernels on the row-stable view of the same entries (built once, cached)
   FSB_TRY(fsb_build_csr_view(A, st));
-  return fsb_launch_csr_spmm(A->view, dY, dX, R, st);
+  return fsb_launch_csr_spmm(A->view, dY, dX, R, st, dZ, lambda);
 }
 
 extern "C" int fsb_tune_formats(int native) {
@@ -369,6 +373,7 @@ int fsb_ata_dev(fsb_matrix_t A, double* dY, const double* dX, int R, double lamb
   if (!dTmp) FSB_TRY(fsb_matrix_scratch(A, (size_t)A->nrow * R * sizeof(double), &dTmp));
   FSB_TRY(fsb_build_transpose(A, st));
   FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
+  if (!dist) return fsb_launch_csr_spmm(A->T, dY, dTmp, R, st, lambda != 0.0 ? dX : nullptr, lambda);   // "+ lambda X" fused
   FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dTmp, R, st));
   FSB_TRY(maybe_allreduce(A, dY, nF, st));
   if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));
@@ -383,6 +388,7 @@ int fsb_ata_pair_dev(fsb_matrix_t A, fsb_matrix_t At, double* dY, const double* 
   cudaStream_t st = fsb_pick_stream(stream);
   if (!dTmp) FSB_TRY(fsb_matrix_scratch(A, (size_t)A->nrow * R * sizeof(double), &dTmp));
   FSB_TRY(spmm_any(A, dTmp, dX, R, st));
+  if (!(A->sharded && fsb_comm_active())) return spmm_any(At, dY, dTmp, R, st, lambda != 0.0 ? dX : nullptr, lambda);   // "+ lambda X" fused
   FSB_TRY(spmm_any(At, dY, dTmp, R, st));
   FSB_TRY(maybe_allreduce(A, dY, (long)A->ncol * R, st));
   if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, (long)A->ncol * R, st));

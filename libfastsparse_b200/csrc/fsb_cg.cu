@@ -3,8 +3,8 @@
 // Replaces bsbm_cg (cg.h:25-82, R = 1) and bsbm_cg2 (cg.h:85-187, R = 2), and
 // generalises the latter to R <= 32 right-hand sides (the reference hard-codes the
 // 2x2 solves; here alpha and psi come from an R x R Cholesky solve on the device).
-// Every vector stays in HBM for the whole solve; per iteration the host reads back
-// two ints (breakdown flag, convergence flag).  With a row-sharded A and an active
+// Every vector stays in HBM for the whole solve; the iteration is predicated on device-side
+// status words, and the host reads them back once per batch of queued iterations.  With a row-sharded A and an active
 // communicator the partial A'(A P) is sum-allreduced inside fsb_ata_*; the dense
 // vectors are replicated and the Gram reductions are deterministic, so all ranks
 // take identical branches without exchanging the flags.
@@ -20,15 +20,17 @@ namespace {
 struct CgWork {
   double *Rm = nullptr, *P = nullptr, *KP = nullptr, *tmp = nullptr;
   double *G1 = nullptr, *G2 = nullptr, *PtKP = nullptr, *Alpha = nullptr, *Psi = nullptr;
-  double *norm = nullptr, *inorm = nullptr, *partial = nullptr;
-  int* status = nullptr;
+  double *norm = nullptr, *inorm = nullptr, *partial = nullptr, *partial2 = nullptr;
+  int* status = nullptr;     // [0] breakdown, [1] converged, [2] completed iterations
   int* h_status = nullptr;
   void release() {
     cudaFree(Rm); cudaFree(P); cudaFree(KP); cudaFree(tmp); cudaFree(G1); cudaFree(G2); cudaFree(PtKP);
-    cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial); cudaFree(status);
+    cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial); cudaFree(partial2); cudaFree(status);
     if (h_status) cudaFreeHost(h_status);
   }
 };
+
+constexpr int kStatusWords = 4;
 
 int cg_alloc(CgWork& w, long F, long N, int R) {
   const size_t fr = std::max<size_t>((size_t)F * R, 1) * 8, nr = std::max<size_t>((size_t)N * R, 1) * 8, rr = (size_t)R * R * 8;
@@ -38,8 +40,9 @@ int cg_alloc(CgWork& w, long F, long N, int R) {
   FSB_CUDA(cudaMalloc(&w.Alpha, rr)); FSB_CUDA(cudaMalloc(&w.Psi, rr));
   FSB_CUDA(cudaMalloc(&w.norm, R * 8)); FSB_CUDA(cudaMalloc(&w.inorm, R * 8));
   FSB_CUDA(cudaMalloc(&w.partial, fsb_dense_gram_scratch_bytes(R)));
-  FSB_CUDA(cudaMalloc(&w.status, 2 * sizeof(int)));
-  FSB_CUDA(cudaMallocHost(&w.h_status, 2 * sizeof(int)));
+  FSB_CUDA(cudaMalloc(&w.partial2, fsb_dense_gram_scratch_bytes(R)));
+  FSB_CUDA(cudaMalloc(&w.status, kStatusWords * sizeof(int)));
+  FSB_CUDA(cudaMallocHost(&w.h_status, kStatusWords * sizeof(int)));
   return FSB_OK;
 }
 
@@ -49,11 +52,29 @@ int apply_op(fsb_matrix* A, fsb_matrix* At, double* KP, const double* P, int R, 
   return fsb_ata_dev(A, KP, P, R, lambda, tmp, 0, (void*)st);
 }
 
+// One iteration, enqueued without looking at the device: every kernel that changes solver state
+// is predicated on status[] (a converged or broken-down solve is left untouched), so the host may
+// queue several iterations per status read-back.  g1 = R'R of the current residual, g2 receives
+// R'R of the next one.
+int cg_enqueue_iteration(fsb_matrix* A, fsb_matrix* At, double* dX, int R, double lambda, double thr, cudaStream_t st,
+                         CgWork& w, double* g1, double* g2) {
+  const long F = A->ncol;
+  int np = 0;
+  FSB_TRY(apply_op(A, At, w.KP, w.P, R, lambda, w.tmp, st));
+  FSB_TRY(fsb_dense_gram_partial(w.partial, w.P, w.KP, F, R, st, &np));                                  // P'KP (first stage)
+  FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, g1, w.partial, np, nullptr, 0, R, w.status, 0, 0.0, st)); // Alpha = PtKP^-1 RtR
+  FSB_TRY(fsb_dense_mix_add(dX, w.P, w.Alpha, F, R, w.status, st));                                      // X += P Alpha
+  FSB_TRY(fsb_dense_mix_sub_gram(w.Rm, w.KP, w.Alpha, w.partial2, F, R, w.status, st, &np));             // R -= KP Alpha, R'R
+  FSB_TRY(fsb_dense_small_solve(w.Psi, g1, g2, nullptr, 0, w.partial2, np, R, w.status, 1, thr, st));    // Psi = RtR^-1 RtR2 (+ stop test)
+  FSB_TRY(fsb_dense_mix_set(w.P, w.P, w.Rm, w.Psi, F, R, w.status, st));                                 // P = R + P Psi
+  return FSB_OK;
+}
+
 int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, double lambda, double tol,
            int max_iter, int* out_iter, cudaStream_t st, CgWork& w) {
   const long F = A->ncol;
   if (max_iter <= 0) max_iter = (int)F;
-  FSB_CUDA(cudaMemsetAsync(w.status, 0, 2 * sizeof(int), st));
+  FSB_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int), st));
   // norms of the right-hand sides; R == 1 keeps the unnormalised recurrence of bsbm_cg
   FSB_TRY(fsb_dense_gram_into(w.G1, w.partial, dB, dB, F, R, st));
   FSB_TRY(fsb_dense_cg_norms(w.norm, w.inorm, w.G1, R, R > 1, st));
@@ -67,28 +88,30 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
     const double t = tol * sqrt(bb);
     thr = t * t;
   }
-  int it = 0;
-  int rc = FSB_OK;
-  for (it = 0; it < max_iter; ++it) {
-    FSB_TRY(apply_op(A, At, w.KP, w.P, R, lambda, w.tmp, st));
-    FSB_TRY(fsb_dense_gram_into(w.PtKP, w.partial, w.P, w.KP, F, R, st));
-    FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, w.G1, R, w.status, 0, 0.0, st));          // Alpha = PtKP^-1 RtR
-    FSB_TRY(fsb_dense_cg_update_xr(dX, w.P, w.Rm, w.KP, w.Alpha, F, R, st));
-    FSB_TRY(fsb_dense_gram_into(w.G2, w.partial, w.Rm, w.Rm, F, R, st));                    // RtR2
-    FSB_TRY(fsb_dense_small_solve(w.Psi, w.G1, w.G2, R, w.status, 1, thr, st));             // Psi = RtR^-1 RtR2 (+ stop test)
-    FSB_CUDA(cudaMemcpyAsync(w.h_status, w.status, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // iterations queued per status read-back: large problems look after every iteration (an
+  // iteration is milliseconds), small ones are launch-latency bound and queue several
+  const double work = (double)A->nnz * R;
+  const int batch = work >= 2e9 ? 1 : (work >= 2e8 ? 2 : 8);
+  int queued = 0;
+  w.h_status[0] = w.h_status[1] = w.h_status[2] = 0;
+  while (queued < max_iter) {
+    const int nb = std::min(batch, max_iter - queued);
+    for (int k = 0; k < nb; ++k) {
+      FSB_TRY(cg_enqueue_iteration(A, At, dX, R, lambda, thr, st, w, w.G1, w.G2));
+      std::swap(w.G1, w.G2);
+    }
+    queued += nb;
+    FSB_CUDA(cudaMemcpyAsync(w.h_status, w.status, kStatusWords * sizeof(int), cudaMemcpyDeviceToHost, st));
     FSB_CUDA(cudaStreamSynchronize(st));
-    if (w.h_status[1]) break;                       // converged (the reference breaks before updating P)
-    if (w.h_status[0]) { rc = FSB_EBREAKDOWN; break; }
-    FSB_TRY(fsb_dense_cg_update_p(w.P, w.Rm, w.Psi, F, R, st));
-    std::swap(w.G1, w.G2);
+    if (w.h_status[0] || w.h_status[1]) break;   // breakdown / converged (the reference breaks before updating P)
   }
+  const int it = w.h_status[2];
   FSB_TRY(fsb_dense_scale_cols(dX, w.norm, F, R, st));
   FSB_CUDA(cudaStreamSynchronize(st));
   if (out_iter) *out_iter = it;
-  if (rc == FSB_EBREAKDOWN)
+  if (w.h_status[0])
     return fsb_set_error(FSB_EBREAKDOWN, "block CG: Gram matrix lost rank at iteration %d (R=%d)", it, R);
-  return rc;
+  return FSB_OK;
 }
 
 }  // namespace

@@ -80,7 +80,10 @@ int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out);
 int fsb_matrix_carry(fsb_matrix* A, size_t bytes, double** out);
 
 // ---- kernels_csr.cu
-int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
+// Y = A X (+ lambda Z when dZ != nullptr; Z is [nrow][R] like Y -- fused into the staged kernel's
+// epilogue, a separate pass for the other kernels)
+int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st, const double* dZ = nullptr,
+                        double lambda = 0.0);
 // ---- kernels_csr_stream.cu (merge-path SpMV / narrow SpMM, R = 1, 2, 4)
 bool fsb_csr_stream_supports(int R);
 bool fsb_csr_stream_preferred(int R);
@@ -90,7 +93,7 @@ int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, 
 void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
 // ---- kernels_csr_staged.cu
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st);
+                               int g, int vec, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0);
 void fsb_csr_staged_set_tuning(int rows_per_cta, int cap_mult);
 
 // ---- kernels_cbcsr.cu / kernels_blocked.cu
@@ -107,7 +110,6 @@ int fsb_stable_perm_by_key(const int* d_keys, int nkeys, long n, int* d_perm, in
 int fsb_blocked_relayout(fsb_matrix* A, cudaStream_t st);  // bucket entries by row class; fills A->row_ptr
 
 // ---- kernels_dense.cu (CG building blocks)
-int fsb_dense_gram(double* dG, const double* dXa, const double* dXb, long n, int R, cudaStream_t st);
 int fsb_dense_axpy_lambda(double* dY, const double* dX, double lambda, long n, cudaStream_t st); // Y += lambda X
 
 // ---- fsb_comm.cu

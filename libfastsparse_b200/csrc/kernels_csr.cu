@@ -296,7 +296,7 @@ int max_row_nnz(fsb_matrix* A, cudaStream_t st, int* out) {
 
 // one product with a fixed configuration (column passes of per_pass columns)
 int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int vec, int per_pass, int g_override,
-               int tw_override, cudaStream_t st) {
+               int tw_override, cudaStream_t st, const double* dZ, double lambda) {
   int g = pow2_ceil((per_pass + vec - 1) / vec);
   if (g_override >= g && g_override <= 32) g = g_override;
   int tw = pick_tw(g, A->avg_row_nnz);
@@ -304,22 +304,29 @@ int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int
   for (int col0 = 0; col0 < R; col0 += per_pass) {
     const int ncols = std::min(per_pass, R - col0);
     if (algo == 2) {
-      FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dX, R, col0, ncols, g, vec, st));
+      FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dX, R, col0, ncols, g, vec, st, dZ, lambda));
       continue;
     }
     if (!dispatch_spmm(tw, g, vec, A, dY, dX, R, col0, ncols, st))
       return fsb_set_error(FSB_EINVAL, "spmm: no kernel for TW=%d G=%d VEC=%d", tw, g, vec);
     FSB_KERNEL_CHECK();
   }
+  if (algo != 2 && dZ) FSB_TRY(fsb_dense_axpy_lambda(dY, dZ, lambda, (long)A->nrow * R, st));   // no fused epilogue in this kernel
+  return FSB_OK;
+}
+
+int stream_config(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st, const double* dZ, double lambda) {
+  FSB_TRY(fsb_launch_csr_stream(A, dY, dX, R, st));
+  if (dZ) FSB_TRY(fsb_dense_axpy_lambda(dY, dZ, lambda, (long)A->nrow * R, st));
   return FSB_OK;
 }
 
 }  // namespace
 
-int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st) {
+int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st, const double* dZ, double lambda) {
   if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
   if (A->nrow == 0) return FSB_OK;
-  const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY;
+  const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY | (uintptr_t)dZ;
   // ---- one right-hand side: the product is bound by the L1 sector-gather rate of x (200 M random
   // 8-byte gathers), so the kernel with the least overhead wins when rows are regular: the
   // team-per-row kernel.  Skewed matrices (a row far longer than the mean, e.g. transposes of
@@ -331,10 +338,10 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
       FSB_TRY(max_row_nnz(A, st, &mx));
       stream = mx > std::max(4096.0, 64.0 * A->avg_row_nnz);
     }
-    if (stream) return fsb_launch_csr_stream(A, dY, dX, R, st);
-    return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st);
+    if (stream) return stream_config(A, dY, dX, R, st, dZ, lambda);
+    return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st, dZ, lambda);
   }
-  if (g_algo == 3 && fsb_csr_stream_supports(R)) return fsb_launch_csr_stream(A, dY, dX, R, st);
+  if (g_algo == 3 && fsb_csr_stream_supports(R)) return stream_config(A, dY, dX, R, st, dZ, lambda);
   const int algo = (g_algo == 1) ? 1 : 2;
   // 128-bit gathers (16 lanes per 256-byte X row) beat the 256-bit form on B200 for the staged
   // kernel at R = 32 (profiles/r1b_sweep_c2_staged_vs_team.json); the 256-bit form is kept for
@@ -345,7 +352,7 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   int per_pass = std::min(R, 32 * vec);
   if (g_slabs >= 1) {   // explicit choice (tools/sweep.py)
     if (g_slabs > 1 && per_pass % (g_slabs * vec) == 0) per_pass /= g_slabs;
-    return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+    return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
   }
   // ---- automatic: when the dense operand does not fit in L2, two column passes of >= 128 B per
   // gather halve the per-pass footprint (more L2 hits) at the price of streaming the indices
@@ -354,15 +361,15 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   // times both (results are identical: each column's sum is untouched) and the handle remembers.
   const bool candidate = algo == 2 && (double)A->ncol * R * 8.0 > 126e6 && per_pass % (2 * vec) == 0 &&
                          per_pass / 2 * 8 >= 128 && A->nnz >= (1 << 22);
-  if (!candidate) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+  if (!candidate) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
   if (A->tuned_R != R) {
     cudaEvent_t ev[3];
     for (auto& e : ev) FSB_CUDA(cudaEventCreate(&e));
     int rc = FSB_OK;
     cudaEventRecord(ev[0], st);
-    rc = run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st);
+    rc = run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
     cudaEventRecord(ev[1], st);
-    if (rc == FSB_OK) rc = run_config(A, dY, dX, R, algo, vec, per_pass / 2, g_g, g_tw, st);
+    if (rc == FSB_OK) rc = run_config(A, dY, dX, R, algo, vec, per_pass / 2, g_g, g_tw, st, dZ, lambda);
     cudaEventRecord(ev[2], st);
     float t1 = 0.f, t2 = 0.f;
     if (rc == FSB_OK && cudaEventSynchronize(ev[2]) == cudaSuccess) {
@@ -374,7 +381,7 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
   }
-  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st);
+  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st, dZ, lambda);
 }
 
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st) {

@@ -29,22 +29,62 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kLongRow = 2048;   // rows at least this long are split across the CTA
 
-#ifndef FSB_STAGED_U
-#define FSB_STAGED_U 8   // gathers in flight per lane (4 -> 8: -3 % single pass, -11 % with two column passes)
+// ---- how the U gathers of a batch are issued (compile-time experiments, tools/sweep.py + FSB_LIB):
+// FSB_STAGED_MINB  min resident CTAs per SM promised to ptxas (0 = none).  With none, ptxas budgets
+//                  32 registers per thread (full occupancy, 8 CTAs/SM) and interleaves each pair of
+//                  gathers with its adds -- about two gathers in flight per lane; with 4 it uses 54
+//                  registers and issues all U gathers back to back (SASS checked).
+// FSB_STAGED_CLAMP 1 = no control flow in the batch: indices past the row end are clamped to the
+//                  row's last entry and the value is zeroed afterwards; 0 = predicated loads.
+// Measured on C2 (profiles/r1f_sweep_c2_gather_issue.md): full occupancy with two gathers in
+// flight (MINB 0, CLAMP 0) is the fastest -- 4.8 ms against 5.35 ms for MINB 4 + CLAMP 1 -- the
+// product is bound by the random-gather throughput of L2/HBM, not by latency, and the clamped
+// form adds ~15 % L1/L2 requests.
+#ifndef FSB_STAGED_MINB
+#define FSB_STAGED_MINB 0
+#endif
+#ifndef FSB_STAGED_CLAMP
+#define FSB_STAGED_CLAMP 0
+#endif
+#if FSB_STAGED_MINB > 0
+#define FSB_STAGED_BOUNDS __launch_bounds__(kThreads, FSB_STAGED_MINB)
+#else
+#define FSB_STAGED_BOUNDS __launch_bounds__(kThreads)
 #endif
 
+#ifndef FSB_STAGED_U
+#define FSB_STAGED_U 8   // gathers per batch and lane
+#endif
+
+// Empty volatile asm that takes a loaded row piece in and out: volatile asms keep their order, so
+// placing these after the U gather asms keeps "all U loads, then the adds" in the emitted PTX.
+template <int VEC> __device__ __forceinline__ void pin_after_loads(double (&x)[VEC]);
+template <> __device__ __forceinline__ void pin_after_loads<1>(double (&x)[1]) { asm volatile("" : "+d"(x[0])); }
+template <> __device__ __forceinline__ void pin_after_loads<2>(double (&x)[2]) { asm volatile("" : "+d"(x[0]), "+d"(x[1])); }
+template <> __device__ __forceinline__ void pin_after_loads<4>(double (&x)[4]) {
+  asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]));
+}
+
+// One row, summed strictly in stored order, gathers issued in batches of U.
 template <int G, int VEC, bool VALS, bool FROM_SMEM>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
-                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok,
+                                         double (&acc)[VEC], const double* __restrict__ xbase, int R,
                                          unsigned long long xpol) {
   constexpr int U = FSB_STAGED_U;
+  const int last = e - 1;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
     double vv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#if FSB_STAGED_CLAMP
+      const int idx = min(i + u, last);
+      const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
+      if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
+      XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
+#else
       const int idx = i + u;
-      if (idx < e && col_ok) {
+      if (idx <= last) {
         const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
         if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
         XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
@@ -53,19 +93,41 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
 #pragma unroll
         for (int v = 0; v < VEC; ++v) xr[u][v] = 0.0;
       }
+#endif
     }
+#if FSB_STAGED_MINB > 0
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) pin_after_loads<VEC>(xr[u]);
+#endif
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] = VALS ? fma(xr[u][v], vv[u], acc[v]) : acc[v] + xr[u][v];
+    for (int u = 0; u < U; ++u) {
+#if FSB_STAGED_CLAMP
+      const bool ok = i + u <= last;
+#else
+      const bool ok = true;
+#endif
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const double term = ok ? xr[u][v] : 0.0;
+        acc[v] = VALS ? fma(term, vv[u], acc[v]) : acc[v] + term;
+      }
+    }
   }
 }
 
+// optional fused epilogue: acc += lambda * Z[row, cols]  (the "+ lambda P" of the CG operator, cg.h:19-21)
+template <int VEC>
+__device__ __forceinline__ void add_scaled_row(double (&acc)[VEC], const double* __restrict__ Z, double lambda, long long off) {
+  if (Z == nullptr) return;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = fma(lambda, __ldg(Z + off + v), acc[v]);
+}
+
 template <int G, int VEC, bool VALS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void FSB_STAGED_BOUNDS
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                       int R, int col0, int ncols, int RB, int CAP, int l2mode) {
+                       int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -81,7 +143,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
   const int r0 = blockIdx.x * RB;
   const int nr = min(RB, nrow - r0);
   const bool col_ok = l * VEC < ncols;
-  const double* xbase = X + col0 + l * VEC;
+  const double* xbase = X + col0 + (col_ok ? l * VEC : 0);   // idle lanes (non-power-of-two widths) re-read lane 0's columns
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
   const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
@@ -101,8 +163,12 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok, xpol);
-      if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
+      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, xpol);
+      if (col_ok) {
+        const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
+        add_scaled_row<VEC>(acc, Z, lambda, off);
+        YStore<VEC>::st(Y + off, acc);
+      }
     }
     return;
   }
@@ -118,7 +184,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, col_ok, xpol);
+      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, xpol);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -129,15 +195,21 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
         for (int t = 0; t < NT; ++t)
 #pragma unroll
           for (int v = 0; v < VEC; ++v) tot[v] += s_red[(t * G + l) * VEC + v];
-        YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, tot);
+        const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
+        add_scaled_row<VEC>(tot, Z, lambda, off);
+        YStore<VEC>::st(Y + off, tot);
       }
       __syncthreads();
     } else if (r % NT == team) {
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, col_ok, xpol);
-      if (col_ok) YStore<VEC>::st(Y + (long long)(r0 + r) * R + col0 + l * VEC, acc);
+      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, xpol);
+      if (col_ok) {
+        const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
+        add_scaled_row<VEC>(acc, Z, lambda, off);
+        YStore<VEC>::st(Y + off, acc);
+      }
     }
   }
 }
@@ -147,28 +219,31 @@ int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <int G, int VEC, bool VALS>
-int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
+int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
+           const double* dZ, double lambda) {
   auto kern = csr_spmm_staged_kernel<G, VEC, VALS>;
   size_t body = std::max((size_t)CAP * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
-  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode);
+  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda);
   return FSB_OK;
 }
 
 template <int G, int VEC>
-int launch_v(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
-  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st)
-                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+int launch_v(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
+             const double* dZ, double lambda) {
+  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda)
+                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
 }
 
 template <int G>
-int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st) {
+int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
+             const double* dZ, double lambda) {
   switch (vec) {
-    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st);
-    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st);
-    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st);
+    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
+    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
+    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
   }
 }
 
@@ -182,7 +257,7 @@ void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
 
 // one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st) {
+                               int g, int vec, cudaStream_t st, const double* dZ, double lambda) {
   // rows per CTA: enough rows that every sub-group gets a few, bounded so that the index
   // run (~avg_nnz * RB entries) stays a small shared-memory footprint (several CTAs per SM)
   const int nt = kThreads / g;
@@ -195,12 +270,12 @@ int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX
   cap = std::max((cap + 63) & ~63, 512);
   int rc;
   switch (g) {
-    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
-    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
-    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
-    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
-    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
-    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st); break;
+    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
   }
   FSB_TRY(rc);
   FSB_KERNEL_CHECK();

@@ -50,8 +50,9 @@ __global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restri
   split[b] = merge_search(row_ptr, nrow, nnz, d);
 }
 
+// (min 4 CTAs/SM: without it ptxas budgets 32 registers and serialises the PER independent loads)
 template <int RT, bool VALS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                   const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                   const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {

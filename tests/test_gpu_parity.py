@@ -356,6 +356,42 @@ def test_linalg_reductions():        # test_sparse.c:511-544
     d = np.zeros(3); fs.pdot2sym(d, gl["X"], gl["Y"], n); assert np.max(np.abs(d - gl["dot2sym"])) < 1e-10
 
 
+@pytest.mark.parametrize("R", [1, 2, 5, 8, 13, 16, 17, 24, 31, 32])
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1000, 40003])
+def test_dense_gram_and_row_mix(R, n):
+    """The tensor-core (DMMA) Gram and row-mix passes of the CG loop (cg.h:148-170, linalg.h:15-73)
+    against numpy fp64, including ragged row counts, every R <= 32 and an unaligned R = 32 operand."""
+    import torch
+    rng = np.random.default_rng(1000 * R + n)
+    L = fs.lib()
+    for shift in ((0, 1) if R == 32 else (0,)):     # shift 1: 8-byte aligned only -> generic (scalar-load) path
+        def dev(a):
+            buf = torch.zeros(a.size + 2, dtype=torch.float64, device="cuda")
+            v = buf[shift:shift + a.size]; v.copy_(torch.from_numpy(a.reshape(-1))); return buf, v
+        I = rng.standard_normal((n, R)); O0 = rng.standard_normal((n, R)); Add = rng.standard_normal((n, R)); M = rng.standard_normal((R, R))
+        _, dM = dev(M)
+        scale = 4.0 * (R + 1)
+        # Gram
+        (_, dI), (_, dA) = dev(I), dev(Add)
+        G = np.zeros((R, R))
+        fs.check(L.fsb_gram_dev(dp(G), dI.data_ptr(), dA.data_ptr(), n, R, None))
+        assert np.max(np.abs(G - I.T @ Add)) <= 1e-12 * max(n, 1) * 16
+        fs.check(L.fsb_gram_dev(dp(G), dI.data_ptr(), dI.data_ptr(), n, R, None))
+        assert np.max(np.abs(G - I.T @ I)) <= 1e-12 * max(n, 1) * 16 and np.array_equal(G, G.T)
+        # mode 0 / 1 / 2
+        _, dO = dev(O0)
+        fs.check(L.fsb_rowmix_dev(0, dO.data_ptr(), dI.data_ptr(), None, dM.data_ptr(), None, n, R, None))
+        assert np.max(np.abs(dO.cpu().numpy().reshape(n, R) - (O0 + I @ M))) <= 1e-13 * scale
+        _, dO = dev(O0)
+        fs.check(L.fsb_rowmix_dev(1, dO.data_ptr(), dI.data_ptr(), None, dM.data_ptr(), dp(G), n, R, None))
+        want = O0 - I @ M
+        assert np.max(np.abs(dO.cpu().numpy().reshape(n, R) - want)) <= 1e-13 * scale
+        assert np.max(np.abs(G - want.T @ want)) <= 1e-12 * max(n, 1) * scale * scale and np.array_equal(G, G.T)
+        _, dP = dev(I)                                # in place: P = Add + P M
+        fs.check(L.fsb_rowmix_dev(2, dP.data_ptr(), dP.data_ptr(), dA.data_ptr(), dM.data_ptr(), None, n, R, None))
+        assert np.max(np.abs(dP.cpu().numpy().reshape(n, R) - (Add + I @ M))) <= 1e-13 * scale
+
+
 # ------------------------------------------------------------------ BASELINE.json full size: size-independent properties
 def test_full_size_c2_properties():
     """C2: binary CSR 10M x 1M, 200M nnz, R = 32.  Checks: (i) a slab of rows against the oracle,
