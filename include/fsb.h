@@ -143,6 +143,18 @@ int fsb_cg_host(fsb_matrix_t A, fsb_matrix_t At, double* X, const double* B, int
 int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const double* dB, int R,
                double lambda, double tol, int max_iter, int* out_iter, void* stream);
 
+/* ------------------------------- Macau-style caller loop */
+/* d[i] = standard normal, a pure function of (seed, i) (counter-based Box-Muller); the host twin
+ * regenerates the same stream (to the last ulps of libm) for checks. */
+int fsb_randn_dev(double* d, long n, unsigned long long seed, void* stream);
+int fsb_randn_host(double* x, long n, unsigned long long seed);
+/* dB[ncol][R] = A'N + sqrt(lambda) E with fresh noise N [nrow][R], E [ncol][R] drawn on the device
+ * (the right-hand side of one sampling step, bench_a_mul_b.c:334-347); A stays resident, the
+ * sqrt(lambda) E term is fused into the A' product.  N = randn(seed ^ k), E = randn(seed + 0x5bd1e995).
+ * Follow with fsb_cg_dev for the solve; repeat with a new seed for the next sample. */
+int fsb_noise_rhs_dev(fsb_matrix_t A, fsb_matrix_t At, double* dB, int R, double lambda,
+                      unsigned long long seed, void* stream);
+
 /* ------------------------------------------- dense helpers (linalg.h) */
 /* G[Ra][Rb] = Xa' Xb over n rows (row-major result, device pointers; out on host).
  * Replaces pnormsq/pnormsq2/pouter2/pdot/pdot2sym linalg.h:15-73. */
@@ -217,6 +229,16 @@ int fsb_host_write_csr_bin(const char* path, const void* struct_image, int nrow,
                            long nnz, const int* row_ptr, const int* cols);
 int fsb_host_read_csr_bin(const char* path, void* struct_image, int* row_ptr, int* cols);
 
+/* ---------------------------------------------- files straight into HBM */
+/* The same files, read in chunks through pinned staging buffers so the H2D copy overlaps the
+ * read, finished on the device; no host copy of the matrix is made.
+ * raw COO (read_sbm sparse.h:112-139 / read_sdm dsparse.h:64-93; with_vals = 1 for the latter)
+ * -> CSR handle, entries of a row in file order exactly like new_bcsr / new_csr of the loaded COO */
+int fsb_csr_load_coo_file(fsb_matrix_t* out, const char* path, int with_vals);
+/* .csr.bin (serialize_to_file csr.h:97-113 / deserialize_from_file csr.h:117-146) -> CSR handle;
+ * struct_image (nullable): receives the file's raw 32-byte struct BinaryCSR */
+int fsb_csr_load_bin_file(fsb_matrix_t* out, const char* path, void* struct_image);
+
 /* ------------------------------------------------- drop-in plumbing */
 /* Used by the drop-in headers in include/fastsparse/.  A handle is cached per host structure, keyed
  * by its array pointers; mutating entry points (sort_*, transpose, free_*)
@@ -245,11 +267,18 @@ int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs);
  * kernel (R = 1, 2, 4; what "automatic" picks for those widths); rows_per_cta and
  * cap_mult (staging capacity = cap_mult * mean entries per CTA) are 0 for automatic */
 int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult);
+/* build of the staged kernel: -1 (default) timed once per handle and R, 0 lean (full occupancy,
+ * ~3 gathers in flight per lane), 1 deep (half occupancy, 8 gathers in flight per lane) */
+int fsb_tune_csr_staged(int deep);
 
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable
  * CSR view of the same entries, built once on the device and cached in the handle;
  * native = 1: the format's own kernels (kernels_blocked.cu, kernels_cbcsr.cu). */
 int fsb_tune_formats(int native);
+/* multi-GPU block CG: 0 (default) = CG vectors sharded over the unknowns (reduce-scatter of the
+ * A'(A P) partial overlapped with its computation, all-gather of P, allreduce of the R x R Grams);
+ * 1 = replicated vectors with one allreduce of the [F][R] partial per iteration. */
+int fsb_tune_cg_dist(int mode);
 
 /* ------------------------------------------ synthetic inputs (bench) */
 /* Counter-based generator: entry j of the COO is a pure function of (seed, j),

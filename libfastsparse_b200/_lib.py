@@ -39,6 +39,8 @@ _SIGS = {
     "fsb_cbcsr_from_coo_dev": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int]),
     "fsb_cbcsr_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, c_int_p, c_int_p]),
     "fsb_blocked_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp]),
+    "fsb_csr_load_coo_file": (C.c_int, [C.POINTER(handle), C.c_char_p, C.c_int]),
+    "fsb_csr_load_bin_file": (C.c_int, [C.POINTER(handle), C.c_char_p, C.c_void_p]),
     "fsb_matrix_free": (C.c_int, [handle]),
     "fsb_matrix_info": (C.c_int, [handle, c_int_p, c_int_p, c_int_p, c_long_p, c_int_p, c_int_p]),
     "fsb_matrix_bytes": (C.c_long, [handle]),
@@ -53,6 +55,9 @@ _SIGS = {
     "fsb_ata_pair_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "fsb_cg_host": (C.c_int, [handle, handle, c_dbl_p, c_dbl_p, C.c_int, C.c_double, C.c_double, C.c_int, c_int_p]),
     "fsb_cg_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, c_int_p, C.c_void_p]),
+    "fsb_randn_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_void_p]),
+    "fsb_randn_host": (C.c_int, [c_dbl_p, C.c_long, C.c_ulonglong]),
+    "fsb_noise_rhs_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_int, C.c_double, C.c_ulonglong, C.c_void_p]),
     "fsb_gram_dev": (C.c_int, [c_dbl_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
     "fsb_gram_host": (C.c_int, [c_dbl_p, c_dbl_p, c_dbl_p, C.c_long, C.c_int]),
     "fsb_rowmix_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_dbl_p, C.c_long, C.c_int, C.c_void_p]),
@@ -92,7 +97,9 @@ _SIGS = {
     "fsb_cache_clear": (None, []),
     "fsb_die": (None, [C.c_char_p]),
     "fsb_tune_csr_spmm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fsb_tune_csr_staged": (C.c_int, [C.c_int]),
     "fsb_tune_formats": (C.c_int, [C.c_int]),
+    "fsb_tune_cg_dist": (C.c_int, [C.c_int]),
     "fsb_tune_csr_algo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fsb_synth_coo_dev": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsb_synth_coo_host": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]),

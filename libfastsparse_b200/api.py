@@ -622,6 +622,20 @@ class DeviceMatrix:
         check(lib().fsb_cbcsr_from_coo_dev(C.byref(h), nrow, ncol, rows.numel(), rows.data_ptr(), cols.data_ptr(), colblocksize))
         return cls(h)
 
+    @classmethod
+    def load_coo_file(cls, path, with_vals=False):
+        """read_sbm / read_sdm file -> HBM-resident CSR, without a host copy of the matrix."""
+        h = handle()
+        check(lib().fsb_csr_load_coo_file(C.byref(h), str(path).encode(), int(with_vals)))
+        return cls(h)
+
+    @classmethod
+    def load_csr_bin(cls, path):
+        """.csr.bin (serialize_to_file) -> HBM-resident binary CSR, without a host copy of the matrix."""
+        h = handle()
+        check(lib().fsb_csr_load_bin_file(C.byref(h), str(path).encode(), None))
+        return cls(h)
+
     def row_slice(self, r0, r1):
         h = handle()
         check(lib().fsb_csr_row_slice(C.byref(h), self.h, int(r0), int(r1)))
@@ -660,6 +674,14 @@ class DeviceMatrix:
             out = torch.empty(self.ncol * R, dtype=torch.float64, device=dX.device)
         check(lib().fsb_ata_dev(self.h, out.data_ptr(), dX.data_ptr(), R, float(lam), tmp.data_ptr() if tmp is not None else None,
                                 mode, _torch_stream()))
+        return out
+
+    def noise_rhs(self, R, lam, seed, At=None, out=None):
+        """B = A'N + sqrt(lam) E with fresh device-generated noise (one Macau sampling step's right-hand side)."""
+        import torch
+        if out is None:
+            out = torch.empty(self.ncol * R, dtype=torch.float64, device="cuda")
+        check(lib().fsb_noise_rhs_dev(self.h, At.h if At is not None else None, out.data_ptr(), R, float(lam), int(seed), _torch_stream()))
         return out
 
     def cg(self, dB, R, lam, tol, At=None, max_iter=0, out=None):

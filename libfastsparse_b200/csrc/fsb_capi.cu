@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <math.h>
 #include <mutex>
 #include <vector>
 
@@ -395,6 +396,45 @@ int fsb_ata_pair_dev(fsb_matrix_t A, fsb_matrix_t At, double* dY, const double* 
   return FSB_OK;
 }
 
+// The right-hand side of a Macau-style sampling step (bench_a_mul_b.c:334-347): B = A'N + sqrt(lambda) E
+// with fresh standard-normal N [nrow][R] and E [ncol][R].  Everything happens in HBM next to the
+// resident matrix: the noise is generated by a counter-based kernel, and sqrt(lambda) E is added in
+// the epilogue of the A' product (no separate axpy pass).  N lives in the handle's scratch buffer.
+int fsb_noise_rhs_dev(fsb_matrix_t A, fsb_matrix_t At, double* dB, int R, double lambda, unsigned long long seed, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (!A || !dB || R < 1 || lambda < 0.0) return fsb_set_error(FSB_EINVAL, "fsb_noise_rhs_dev: bad argument");
+  if (!At && A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_noise_rhs_dev: a stored transpose is required for non-CSR formats");
+  if (At && (A->nrow != At->ncol || A->ncol != At->nrow))
+    return fsb_set_error(FSB_EINVAL, "A (%d x %d) and At (%d x %d) must be transposes of each other.", A->nrow, A->ncol, At->nrow, At->ncol);
+  cudaStream_t st = fsb_pick_stream(stream);
+  const long nN = (long)A->nrow * R, nF = (long)A->ncol * R;
+  double *dN = nullptr, *dE = nullptr;
+  FSB_TRY(fsb_matrix_scratch(A, (size_t)std::max(nN, 1L) * sizeof(double), &dN));
+  FSB_CUDA(cudaMalloc(&dE, (size_t)std::max(nF, 1L) * sizeof(double)));
+  // every rank of a row-sharded solve draws its own N rows (seed offset by the rank) and the same E
+  const unsigned long long nseed = seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(A->sharded ? fsb_comm_rank() + 1 : 1));
+  int rc = fsb_randn_dev(dN, nN, nseed, (void*)st);
+  if (rc == FSB_OK) rc = fsb_randn_dev(dE, nF, seed + 0x5bd1e995ull, (void*)st);
+  const double s = sqrt(lambda);
+  if (rc == FSB_OK) {
+    if (!At) rc = fsb_build_transpose(A, st);
+    fsb_matrix* T = At ? At : A->T;
+    if (rc == FSB_OK) {
+      if (A->sharded && fsb_comm_active()) {
+        rc = spmm_any(T, dB, dN, R, st);
+        if (rc == FSB_OK) rc = maybe_allreduce(A, dB, nF, st);
+        if (rc == FSB_OK && s != 0.0) rc = fsb_dense_axpy_lambda(dB, dE, s, nF, st);
+      } else {
+        rc = spmm_any(T, dB, dN, R, st, s != 0.0 ? dE : nullptr, s);
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);   // dE is released below
+  cudaFree(dE);
+  if (rc == FSB_OK && e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_noise_rhs_dev", __FILE__, __LINE__);
+  return rc;
+}
+
 }  // extern "C"
 
 // ---- host-pointer products: stage X in, run, stage Y out.  Large outputs are
@@ -453,10 +493,10 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
       fsb_matrix part;                 // rows [r0, r1): row_ptr values stay absolute, so cols/vals are shared
       part.format = FSB_FMT_CSR; part.nrow = r1 - r0; part.ncol = C->ncol; part.nnz = C->nnz; part.has_vals = C->has_vals;
       part.row_ptr = C->row_ptr + r0; part.cols = C->cols; part.vals = C->vals; part.avg_row_nnz = C->avg_row_nnz;
-      part.tuned_R = C->tuned_R; part.tuned_passes = C->tuned_passes;   // share the handle's autotune decision
+      fsb_copy_tuning(&part, C);   // share the handle's autotune decision
       double* dYc = g_stage.dY + (size_t)r0 * R;
       FSB_TRY(fsb_launch_csr_spmm(&part, dYc, g_stage.dX, R, g_stream));
-      C->tuned_R = part.tuned_R; C->tuned_passes = part.tuned_passes;
+      fsb_copy_tuning(C, &part);
       FSB_CUDA(cudaEventRecord(g_stage.ev[c & 1], g_stream));
       FSB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_stage.ev[c & 1], 0));
       FSB_CUDA(cudaMemcpyAsync(Y + (size_t)r0 * R, dYc, (size_t)(r1 - r0) * R * 8, cudaMemcpyDeviceToHost, g_copy_stream));

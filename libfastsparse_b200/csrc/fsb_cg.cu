@@ -9,6 +9,10 @@
 // vectors are replicated and the Gram reductions are deterministic, so all ranks
 // take identical branches without exchanging the flags.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include <algorithm>
 
@@ -16,6 +20,16 @@
 #include "fsb_internal.h"
 
 namespace {
+
+// FSB_CG_TRACE=1: wall-clock milliseconds of the solve's phases on stderr (allocation, set-up, every
+// status read-back) -- a debugging aid for gaps the kernel timings do not show
+bool cg_trace() {
+  static const bool on = [] { const char* e = getenv("FSB_CG_TRACE"); return e && *e && *e != '0'; }();
+  return on;
+}
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct CgWork {
   double *Rm = nullptr, *P = nullptr, *KP = nullptr, *tmp = nullptr;
@@ -94,6 +108,8 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
   const int batch = work >= 2e9 ? 1 : (work >= 2e8 ? 2 : 8);
   int queued = 0;
   w.h_status[0] = w.h_status[1] = w.h_status[2] = 0;
+  double t_prev = 0.0;
+  if (cg_trace()) { cudaStreamSynchronize(st); t_prev = now_ms(); }
   while (queued < max_iter) {
     const int nb = std::min(batch, max_iter - queued);
     for (int k = 0; k < nb; ++k) {
@@ -103,6 +119,11 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
     queued += nb;
     FSB_CUDA(cudaMemcpyAsync(w.h_status, w.status, kStatusWords * sizeof(int), cudaMemcpyDeviceToHost, st));
     FSB_CUDA(cudaStreamSynchronize(st));
+    if (cg_trace()) {
+      const double t = now_ms();
+      fprintf(stderr, "[fsb cg] iterations %d..%d: %.3f ms (status %d %d %d)\n", queued - nb, queued - 1, t - t_prev, w.h_status[0], w.h_status[1], w.h_status[2]);
+      t_prev = t;
+    }
     if (w.h_status[0] || w.h_status[1]) break;   // breakdown / converged (the reference breaks before updating P)
   }
   const int it = w.h_status[2];
@@ -114,7 +135,216 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
   return FSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-GPU solve: A is row-sharded (rank g holds rows of A and the transpose of its shard), the
+// CG vectors are sharded over the F unknowns.  Per iteration:
+//   tmp_g  = A_g P                    P replicated ([F][R], all-gathered at the end of the previous iteration)
+//   part_g = A_g' tmp_g               full-length partial, produced in C row chunks;
+//   KP_loc = reduce-scatter(part)     chunk c is reduce-scattered on a second stream while chunk c+1 is
+//                                     still being computed (the transfer hides behind the product)
+//   Grams  = allreduce of R x R       identical bits on every rank => identical branches everywhere
+//   X, R, P updates on the local 1/G of the rows; all-gather of the new P.
+// The F rows are cut into C chunks of Fc rows, every chunk into G slices of s rows; rank g owns slice g
+// of every chunk (local layout [C][s][R]).  The dense passes are row-local, so the layout is invisible
+// to them.  Rows are padded with zeros to C*G*s.
+constexpr int kMaxChunks = 4;
+
+struct CgShardWork {
+  int G = 1, rank = 0, C = 1;
+  long F = 0, Fc = 0, s = 0, Fp = 0, nloc = 0;
+  double *Pfull = nullptr, *KPpart = nullptr, *Xl = nullptr, *Rl = nullptr, *Pl = nullptr, *KPl = nullptr, *tmp = nullptr;
+  double *G1 = nullptr, *G2 = nullptr, *PtKP = nullptr, *Alpha = nullptr, *Psi = nullptr, *norm = nullptr, *inorm = nullptr;
+  double *partial = nullptr;
+  int *status = nullptr, *h_status = nullptr;
+  cudaStream_t comm_st = nullptr;
+  cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;
+  void release() {
+    cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
+    cudaFree(G1); cudaFree(G2); cudaFree(PtKP); cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial);
+    cudaFree(status);
+    if (h_status) cudaFreeHost(h_status);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (comm_st) cudaStreamDestroy(comm_st);
+  }
+};
+
+int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
+  w.G = fsb_comm_size(); w.rank = fsb_comm_rank(); w.F = F;
+  // chunks only pay off when a chunk is a sizeable transfer; R = 1 keeps one chunk (its products may
+  // take the merge-path kernel, which caches per-handle state and must see the whole matrix)
+  w.C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? kMaxChunks : 1;
+  w.s = (F + (long)w.C * w.G - 1) / ((long)w.C * w.G);
+  if ((w.s * R) % 2) w.s += 1;            // keep every slice 16-byte aligned for the vector paths
+  w.Fc = w.s * w.G; w.Fp = w.Fc * w.C; w.nloc = w.s * w.C;
+  const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8, rr = (size_t)R * R * 8;
+  FSB_CUDA(cudaMalloc(&w.Pfull, full)); FSB_CUDA(cudaMalloc(&w.KPpart, full));
+  FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
+  FSB_CUDA(cudaMalloc(&w.tmp, std::max<size_t>((size_t)Nloc * R, 1) * 8));
+  FSB_CUDA(cudaMalloc(&w.G1, rr)); FSB_CUDA(cudaMalloc(&w.G2, rr)); FSB_CUDA(cudaMalloc(&w.PtKP, rr));
+  FSB_CUDA(cudaMalloc(&w.Alpha, rr)); FSB_CUDA(cudaMalloc(&w.Psi, rr));
+  FSB_CUDA(cudaMalloc(&w.norm, R * 8)); FSB_CUDA(cudaMalloc(&w.inorm, R * 8));
+  FSB_CUDA(cudaMalloc(&w.partial, fsb_dense_gram_scratch_bytes(R)));
+  FSB_CUDA(cudaMalloc(&w.status, kStatusWords * sizeof(int)));
+  FSB_CUDA(cudaMallocHost(&w.h_status, kStatusWords * sizeof(int)));
+  FSB_CUDA(cudaStreamCreateWithFlags(&w.comm_st, cudaStreamNonBlocking));
+  for (auto& e : w.ev) FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
+  return FSB_OK;
+}
+
+// the CSR face of a handle (blocked / column-blocked formats: their cached row-stable CSR view)
+int csr_face(fsb_matrix* M, cudaStream_t st, fsb_matrix** out) {
+  if (M->format == FSB_FMT_CSR) { *out = M; return FSB_OK; }
+  FSB_TRY(fsb_build_csr_view(M, st));
+  *out = M->view;
+  return FSB_OK;
+}
+
+// G (R x R) = sum over ranks of Xa_loc' Xb_loc
+int shard_gram(CgShardWork& w, double* G, const double* Xa, const double* Xb, int R, cudaStream_t st) {
+  FSB_TRY(fsb_dense_gram_into(G, w.partial, Xa, Xb, w.nloc, R, st));
+  return fsb_allreduce_sum_dev(G, (long)R * R, (void*)st);
+}
+
+// all-gather the local slices of every chunk of a sharded vector into the replicated layout
+int shard_allgather(CgShardWork& w, double* full, const double* loc, int R, cudaStream_t st) {
+  for (int c = 0; c < w.C; ++c)
+    FSB_TRY(fsb_comm_allgather(loc + (size_t)c * w.s * R, full + (size_t)c * w.Fc * R, (size_t)w.s * R, st));
+  return FSB_OK;
+}
+
+// KP_loc = slice of sum_g A_g'(A_g P) + lambda P_loc
+int shard_apply_op(fsb_matrix* A, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st) {
+  FSB_TRY(fsb_spmm_dev(A, w.tmp, w.Pfull, R, (void*)st));
+  for (int c = 0; c < w.C; ++c) {
+    const long r0 = c * w.Fc, r1 = std::min(w.F, r0 + w.Fc);
+    if (r1 > r0) {
+      if (w.C == 1) {
+        FSB_TRY(fsb_launch_csr_spmm(T, w.KPpart, w.tmp, R, st));
+      } else {
+        fsb_matrix part;     // rows [r0, r1) of A_g': row_ptr values stay absolute, so cols / vals are shared
+        part.format = FSB_FMT_CSR; part.nrow = (int)(r1 - r0); part.ncol = T->ncol; part.nnz = T->nnz; part.has_vals = T->has_vals;
+        part.row_ptr = T->row_ptr + r0; part.cols = T->cols; part.vals = T->vals; part.avg_row_nnz = T->avg_row_nnz;
+        fsb_copy_tuning(&part, T);
+        FSB_TRY(fsb_launch_csr_spmm(&part, w.KPpart + (size_t)r0 * R, w.tmp, R, st));
+        fsb_copy_tuning(T, &part);
+      }
+    }
+    FSB_CUDA(cudaEventRecord(w.ev[c], st));
+    FSB_CUDA(cudaStreamWaitEvent(w.comm_st, w.ev[c], 0));
+    FSB_TRY(fsb_comm_reduce_scatter_sum(w.KPpart + (size_t)c * w.Fc * R, w.KPl + (size_t)c * w.s * R, (size_t)w.s * R, w.comm_st));
+  }
+  FSB_CUDA(cudaEventRecord(w.ev_done, w.comm_st));
+  FSB_CUDA(cudaStreamWaitEvent(st, w.ev_done, 0));
+  if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(w.KPl, w.Pl, lambda, w.nloc * R, st));
+  return FSB_OK;
+}
+
+int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, double lambda, double tol,
+                   int max_iter, int* out_iter, cudaStream_t st, CgShardWork& w) {
+  const long F = A->ncol;
+  if (max_iter <= 0) max_iter = (int)F;
+  fsb_matrix* T = nullptr;
+  if (At) {
+    FSB_TRY(csr_face(At, st, &T));
+  } else {
+    FSB_TRY(fsb_build_transpose(A, st));
+    T = A->T;
+  }
+  const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8;
+  FSB_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int), st));
+  FSB_CUDA(cudaMemsetAsync(w.KPpart, 0, full, st));     // the padding rows stay zero for the whole solve
+  FSB_CUDA(cudaMemsetAsync(w.Xl, 0, loc, st)); FSB_CUDA(cudaMemsetAsync(w.Rl, 0, loc, st)); FSB_CUDA(cudaMemsetAsync(w.Pl, 0, loc, st));
+  // column norms from the replicated right-hand side (every rank computes the same bits)
+  FSB_TRY(fsb_dense_gram_into(w.G1, w.partial, dB, dB, F, R, st));
+  FSB_TRY(fsb_dense_cg_norms(w.norm, w.inorm, w.G1, R, R > 1, st));
+  for (int c = 0; c < w.C; ++c) {   // X = 0, R = P = B diag(inorm) on the local slices
+    const long g0 = c * w.Fc + w.rank * w.s;
+    const long valid = std::max(0L, std::min(w.s, F - g0));
+    const size_t lo = (size_t)c * w.s * R;
+    if (valid > 0) FSB_TRY(fsb_dense_cg_init(w.Xl + lo, w.Rl + lo, w.Pl + lo, dB + (size_t)g0 * R, w.inorm, valid, R, st));
+  }
+  FSB_TRY(shard_allgather(w, w.Pfull, w.Pl, R, st));
+  FSB_TRY(shard_gram(w, w.G1, w.Rl, w.Rl, R, st));   // RtR
+  double thr = tol * tol;
+  if (R == 1) {
+    double bb = 0.0;
+    FSB_CUDA(cudaMemcpyAsync(&bb, w.G1, 8, cudaMemcpyDeviceToHost, st));
+    FSB_CUDA(cudaStreamSynchronize(st));
+    const double t = tol * sqrt(bb);
+    thr = t * t;
+  }
+  const double work = (double)A->nnz * R;
+  const int batch = work >= 2e8 ? 1 : 4;
+  int queued = 0, np = 0;
+  w.h_status[0] = w.h_status[1] = w.h_status[2] = 0;
+  while (queued < max_iter) {
+    const int nb = std::min(batch, max_iter - queued);
+    for (int k = 0; k < nb; ++k) {
+      FSB_TRY(shard_apply_op(A, T, w, R, lambda, st));
+      FSB_TRY(shard_gram(w, w.PtKP, w.Pl, w.KPl, R, st));
+      FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, w.G1, nullptr, 0, nullptr, 0, R, w.status, 0, 0.0, st));
+      FSB_TRY(fsb_dense_mix_add(w.Xl, w.Pl, w.Alpha, w.nloc, R, w.status, st));
+      FSB_TRY(fsb_dense_mix_sub_gram(w.Rl, w.KPl, w.Alpha, w.partial, w.nloc, R, w.status, st, &np));
+      FSB_TRY(fsb_dense_gram_finalize(w.G2, w.partial, np, R, st));
+      FSB_TRY(fsb_allreduce_sum_dev(w.G2, (long)R * R, (void*)st));
+      FSB_TRY(fsb_dense_small_solve(w.Psi, w.G1, w.G2, nullptr, 0, nullptr, 0, R, w.status, 1, thr, st));
+      FSB_TRY(fsb_dense_mix_set(w.Pl, w.Pl, w.Rl, w.Psi, w.nloc, R, w.status, st));
+      FSB_TRY(shard_allgather(w, w.Pfull, w.Pl, R, st));
+      std::swap(w.G1, w.G2);
+    }
+    queued += nb;
+    FSB_CUDA(cudaMemcpyAsync(w.h_status, w.status, kStatusWords * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FSB_CUDA(cudaStreamSynchronize(st));
+    if (w.h_status[0] || w.h_status[1]) break;
+  }
+  const int it = w.h_status[2];
+  // X = X_loc diag(norm), gathered into the replicated result (through the partial buffer: padded rows)
+  for (int c = 0; c < w.C; ++c) FSB_TRY(fsb_dense_scale_cols(w.Xl + (size_t)c * w.s * R, w.norm, w.s, R, st));
+  FSB_TRY(shard_allgather(w, w.KPpart, w.Xl, R, st));
+  FSB_CUDA(cudaMemcpyAsync(dX, w.KPpart, (size_t)F * R * 8, cudaMemcpyDeviceToDevice, st));
+  FSB_CUDA(cudaStreamSynchronize(st));
+  if (out_iter) *out_iter = it;
+  if (w.h_status[0])
+    return fsb_set_error(FSB_EBREAKDOWN, "block CG: Gram matrix lost rank at iteration %d (R=%d)", it, R);
+  return FSB_OK;
+}
+
+int g_cg_dist_mode = 0;   // 0 = sharded vectors when a communicator is active, 1 = replicated vectors + allreduce
+
+// one solve through whichever path applies to the handle
+int cg_solve(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, double lambda, double tol, int max_iter,
+             int* out_iter, cudaStream_t st) {
+  const bool shard = A->sharded && fsb_comm_active() && g_cg_dist_mode == 0 && (long)A->ncol >= 64L * fsb_comm_size();
+  int rc;
+  if (shard) {
+    CgShardWork w;
+    rc = shard_alloc(w, A->ncol, A->nrow, R);
+    if (rc == FSB_OK) rc = cg_run_sharded(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, w);
+    cudaStreamSynchronize(w.comm_st ? w.comm_st : st);
+    w.release();
+  } else {
+    CgWork w;
+    const double t0 = cg_trace() ? now_ms() : 0.0;
+    rc = cg_alloc(w, A->ncol, A->nrow, R);
+    const double t1 = cg_trace() ? now_ms() : 0.0;
+    if (rc == FSB_OK) rc = cg_run(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, w);
+    const double t2 = cg_trace() ? now_ms() : 0.0;
+    w.release();
+    if (cg_trace()) fprintf(stderr, "[fsb cg] alloc %.3f ms, solve %.3f ms, release %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
+  }
+  return rc;
+}
+
 }  // namespace
+
+extern "C" int fsb_tune_cg_dist(int mode) {
+  if (mode < 0 || mode > 1) return fsb_set_error(FSB_EINVAL, "fsb_tune_cg_dist: mode must be 0 (sharded vectors) or 1 (replicated)");
+  g_cg_dist_mode = mode;
+  return FSB_OK;
+}
 
 extern "C" int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const double* dB, int R, double lambda,
                           double tol, int max_iter, int* out_iter, void* stream) {
@@ -125,9 +355,7 @@ extern "C" int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const dou
     return fsb_set_error(FSB_EINVAL, "A (%d x %d) and At (%d x %d) must be transposes of each other.", A->nrow, A->ncol, At->nrow, At->ncol);
   if (!At && A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_cg_dev: a stored transpose is required for non-CSR formats");
   cudaStream_t st = fsb_pick_stream(stream);
-  CgWork w;
-  int rc = cg_alloc(w, A->ncol, A->nrow, R);
-  if (rc == FSB_OK) rc = cg_run(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, w);
+  int rc = cg_solve(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st);
   if (rc == FSB_EBREAKDOWN && R > 1) {
     // rank loss (a column converged early / dependent right-hand sides): the block
     // recurrence cannot continue; solve the columns one by one instead
@@ -137,13 +365,11 @@ extern "C" int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const dou
     cudaError_t e = cudaMalloc(&xb, std::max<size_t>(F, 1) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&bb, std::max<size_t>(F, 1) * 8);
     rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
-    CgWork w1;
-    if (rc == FSB_OK) rc = cg_alloc(w1, A->ncol, A->nrow, 1);
     for (int k = 0; rc == FSB_OK && k < R; ++k) {
       e = cudaMemcpy2DAsync(bb, 8, dB + k, (size_t)R * 8, 8, F, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) { rc = fsb_cuda_error(e, "column gather", __FILE__, __LINE__); break; }
       int it1 = 0;
-      rc = cg_run(A, At, xb, bb, 1, lambda, tol, max_iter, &it1, st, w1);
+      rc = cg_solve(A, At, xb, bb, 1, lambda, tol, max_iter, &it1, st);
       worst = std::max(worst, it1);
       if (rc == FSB_OK) {
         e = cudaMemcpy2DAsync(dX + k, (size_t)R * 8, xb, 8, 8, F, cudaMemcpyDeviceToDevice, st);
@@ -155,10 +381,8 @@ extern "C" int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const dou
       if (e != cudaSuccess) rc = fsb_cuda_error(e, "sync", __FILE__, __LINE__);
     }
     if (out_iter) *out_iter = worst;
-    w1.release();
     cudaFree(xb); cudaFree(bb);
   }
-  w.release();
   return rc;
 }
 

@@ -20,6 +20,8 @@ typedef void* nccl_comm;
 typedef int (*fn_get_uid)(nccl_uid*);
 typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef int (*fn_reduce_scatter)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
 typedef int (*fn_destroy)(nccl_comm);
 typedef const char* (*fn_errstr)(int);
 
@@ -28,6 +30,8 @@ struct Nccl {
   fn_get_uid get_uid = nullptr;
   fn_init_rank init_rank = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_reduce_scatter reduce_scatter = nullptr;
+  fn_allgather allgather = nullptr;
   fn_destroy destroy = nullptr;
   fn_errstr errstr = nullptr;
 } g_nccl;
@@ -47,9 +51,11 @@ int load_nccl() {
   g_nccl.get_uid = (fn_get_uid)dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.init_rank = (fn_init_rank)dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.reduce_scatter = (fn_reduce_scatter)dlsym(g_nccl.lib, "ncclReduceScatter");
+  g_nccl.allgather = (fn_allgather)dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
-  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy) {
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.reduce_scatter || !g_nccl.allgather || !g_nccl.destroy) {
     g_nccl.lib = nullptr;
     return fsb_set_error(FSB_ENCCL, "libnccl is missing a required symbol");
   }
@@ -63,6 +69,20 @@ int nccl_fail(int code, const char* what) {
 }  // namespace
 
 bool fsb_comm_active() { return g_comm != nullptr && g_nranks > 1; }
+
+// recv[recvcount] = this rank's slice of the element-wise sum of every rank's send[nranks*recvcount]
+int fsb_comm_reduce_scatter_sum(const double* send, double* recv, size_t recvcount, cudaStream_t st) {
+  if (!fsb_comm_active()) return fsb_set_error(FSB_ENCCL, "reduce-scatter without an active communicator");
+  const int rc = g_nccl.reduce_scatter(send, recv, recvcount, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_comm, st);
+  return rc ? nccl_fail(rc, "ncclReduceScatter") : FSB_OK;
+}
+
+// recv[nranks*sendcount] = concatenation of every rank's send[sendcount] in rank order
+int fsb_comm_allgather(const double* send, double* recv, size_t sendcount, cudaStream_t st) {
+  if (!fsb_comm_active()) return fsb_set_error(FSB_ENCCL, "all-gather without an active communicator");
+  const int rc = g_nccl.allgather(send, recv, sendcount, /*ncclFloat64*/ 8, g_comm, st);
+  return rc ? nccl_fail(rc, "ncclAllGather") : FSB_OK;
+}
 
 extern "C" {
 

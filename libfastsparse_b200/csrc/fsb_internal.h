@@ -40,8 +40,9 @@ struct fsb_matrix {
   int* split = nullptr;       // cached merge-path tile boundaries (rows complete at each tile start)
   int split_tile = 0;
   int max_row_nnz = -1;       // longest row (lazy; SpMV kernel choice)
-  int tuned_R = 0;            // column-pass autotune of the staged SpMM (see fsb_launch_csr_spmm)
-  int tuned_passes = 1;
+  int tuned_R = 0;            // autotune of the staged SpMM (see fsb_launch_csr_spmm): valid for this R,
+  int tuned_passes = 1;       //   column passes over the dense operand (1 or 2)
+  int tuned_deep = 0;         //   lean (0) or deep (1) build of the kernel
   size_t bytes = 0;
   double avg_row_nnz = 0.0;
 };
@@ -93,7 +94,11 @@ int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, 
 void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
 // ---- kernels_csr_staged.cu
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0);
+                               int g, int vec, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0, bool deep = false);
+// a row-range alias of a CSR handle (row_ptr offset, shared cols / vals) inherits and returns the autotune state
+inline void fsb_copy_tuning(fsb_matrix* dst, const fsb_matrix* src) {
+  dst->tuned_R = src->tuned_R; dst->tuned_passes = src->tuned_passes; dst->tuned_deep = src->tuned_deep;
+}
 void fsb_csr_staged_set_tuning(int rows_per_cta, int cap_mult);
 
 // ---- kernels_cbcsr.cu / kernels_blocked.cu
@@ -114,3 +119,5 @@ int fsb_dense_axpy_lambda(double* dY, const double* dX, double lambda, long n, c
 
 // ---- fsb_comm.cu
 bool fsb_comm_active();
+int fsb_comm_reduce_scatter_sum(const double* send, double* recv, size_t recvcount, cudaStream_t st);
+int fsb_comm_allgather(const double* send, double* recv, size_t sendcount, cudaStream_t st);

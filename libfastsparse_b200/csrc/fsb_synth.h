@@ -62,3 +62,16 @@ FSB_HD int fsb_synth_col(uint64_t seed, uint64_t j, int ncol, int dist) {
 FSB_HD double fsb_synth_val(uint64_t seed, uint64_t j) {
   return (double)(fsb_mix64(seed ^ (3 * j + 2)) >> 11) * (1.0 / 9007199254740992.0);
 }
+
+// standard normal N(0,1), element i a pure function of (seed, i): Box-Muller on two 53-bit
+// uniforms.  (The reference's randn, bench_a_mul_b.c:43-60, is the polar method on erand48 --
+// a sequential stream; a counter-based one lets every GPU thread, and the host-side check,
+// regenerate any element.)  Host and device agree to the last ulps of log / cos.
+#if defined(__CUDACC__) || defined(FSB_SYNTH_WITH_MATH)
+#include <math.h>
+FSB_HD double fsb_synth_normal(uint64_t seed, uint64_t i) {
+  const double u1 = (double)((fsb_mix64(seed ^ (2 * i)) >> 11) + 1) * (1.0 / 9007199254740992.0);       // (0, 1]
+  const double u2 = (double)(fsb_mix64(seed ^ (2 * i + 1)) >> 11) * (1.0 / 9007199254740992.0);         // [0, 1)
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+}
+#endif

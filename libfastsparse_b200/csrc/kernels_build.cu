@@ -476,6 +476,29 @@ extern "C" int fsb_synth_coo_dev(unsigned long long seed, int dist, long nnz, in
   return FSB_OK;
 }
 
+namespace {
+__global__ void randn_kernel(double* __restrict__ d, long long n, unsigned long long seed) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = fsb_synth_normal(seed, (unsigned long long)i);
+}
+}  // namespace
+
+extern "C" int fsb_randn_dev(double* d, long n, unsigned long long seed, void* stream) {
+  FSB_TRY(fsb_require_device());
+  if (n < 0 || (n > 0 && !d)) return fsb_set_error(FSB_EINVAL, "fsb_randn_dev: bad arguments");
+  if (n == 0) return FSB_OK;
+  randn_kernel<<<grid_for(n), 256, 0, fsb_pick_stream(stream)>>>(d, n, seed);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+extern "C" int fsb_randn_host(double* x, long n, unsigned long long seed) {
+  if (n < 0 || (n > 0 && !x)) return fsb_set_error(FSB_EINVAL, "fsb_randn_host: bad arguments");
+  for (long i = 0; i < n; ++i) x[i] = fsb_synth_normal(seed, (unsigned long long)i);
+  return FSB_OK;
+}
+
 extern "C" int fsb_synth_coo_host(unsigned long long seed, int dist, long nnz, int nrow, int ncol,
                                   int* rows, int* cols, double* vals) {
   if (nnz < 0 || nrow <= 0 || ncol <= 0 || !rows || !cols) return fsb_set_error(FSB_EINVAL, "synth: bad arguments");

@@ -254,6 +254,14 @@ extern "C" int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult) {
   return FSB_OK;
 }
 
+int g_deep = -1;   // staged kernel build: -1 automatic (timed per handle), 0 lean, 1 deep
+
+extern "C" int fsb_tune_csr_staged(int deep) {
+  if (deep < -1 || deep > 1) return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_staged: deep must be -1, 0 or 1");
+  g_deep = deep;
+  return FSB_OK;
+}
+
 extern "C" int fsb_tune_csr_spmm(int tw, int g, int vec, int slabs) {
   auto pow2 = [](int x) { return x == 0 || (x > 0 && x <= 32 && (x & (x - 1)) == 0); };
   if (!pow2(tw) || !pow2(g) || !(vec == 0 || vec == 1 || vec == 2 || vec == 4) || slabs < 0)
@@ -296,7 +304,7 @@ int max_row_nnz(fsb_matrix* A, cudaStream_t st, int* out) {
 
 // one product with a fixed configuration (column passes of per_pass columns)
 int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int vec, int per_pass, int g_override,
-               int tw_override, cudaStream_t st, const double* dZ, double lambda) {
+               int tw_override, cudaStream_t st, const double* dZ, double lambda, bool deep = false) {
   int g = pow2_ceil((per_pass + vec - 1) / vec);
   if (g_override >= g && g_override <= 32) g = g_override;
   int tw = pick_tw(g, A->avg_row_nnz);
@@ -304,7 +312,7 @@ int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int
   for (int col0 = 0; col0 < R; col0 += per_pass) {
     const int ncols = std::min(per_pass, R - col0);
     if (algo == 2) {
-      FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dX, R, col0, ncols, g, vec, st, dZ, lambda));
+      FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dX, R, col0, ncols, g, vec, st, dZ, lambda, deep));
       continue;
     }
     if (!dispatch_spmm(tw, g, vec, A, dY, dX, R, col0, ncols, st))
@@ -352,36 +360,48 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   int per_pass = std::min(R, 32 * vec);
   if (g_slabs >= 1) {   // explicit choice (tools/sweep.py)
     if (g_slabs > 1 && per_pass % (g_slabs * vec) == 0) per_pass /= g_slabs;
-    return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
+    return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda, g_deep > 0);
   }
-  // ---- automatic: when the dense operand does not fit in L2, two column passes of >= 128 B per
-  // gather halve the per-pass footprint (more L2 hits) at the price of streaming the indices
-  // twice.  That is 15 % faster on uniform columns and 25 % slower on power-law columns (whose hot
-  // columns hit L2 anyway) -- not predictable from the shape, so the first product on a handle
-  // times both (results are identical: each column's sum is untouched) and the handle remembers.
-  const bool candidate = algo == 2 && (double)A->ncol * R * 8.0 > 126e6 && per_pass % (2 * vec) == 0 &&
-                         per_pass / 2 * 8 >= 128 && A->nnz >= (1 << 22);
-  if (!candidate) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
+  // ---- automatic.  Two choices are not predictable from the shape, so the first product on a
+  // handle (per R) times the candidates -- every one produces the identical result, each column's
+  // sum is taken in the same order -- and the handle remembers the fastest:
+  //  * column passes: when the dense operand does not fit in L2, two passes of >= 128 B per gather
+  //    halve the per-pass footprint (more L2 hits) at the price of streaming the indices twice:
+  //    faster on uniform columns, slower on power-law columns (whose hot rows hit L2 anyway);
+  //  * lean or deep build of the staged kernel (kernels_csr_staged.cu): occupancy vs gathers in
+  //    flight per lane.
+  const bool big = algo == 2 && A->nnz >= (1 << 22);
+  if (!big) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda, g_deep > 0);
+  const bool two_pass_ok = (double)A->ncol * R * 8.0 > 126e6 && per_pass % (2 * vec) == 0 && per_pass / 2 * 8 >= 128;
   if (A->tuned_R != R) {
-    cudaEvent_t ev[3];
+    struct Cand { int passes; bool deep; float ms; };
+    Cand cand[4];
+    int nc = 0;
+    for (int passes = 1; passes <= (two_pass_ok ? 2 : 1); ++passes)
+      for (int deep = 0; deep <= 1; ++deep)
+        if (g_deep < 0 || g_deep == deep) cand[nc++] = {passes, deep != 0, 0.f};
+    cudaEvent_t ev[5];
     for (auto& e : ev) FSB_CUDA(cudaEventCreate(&e));
     int rc = FSB_OK;
     cudaEventRecord(ev[0], st);
-    rc = run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda);
-    cudaEventRecord(ev[1], st);
-    if (rc == FSB_OK) rc = run_config(A, dY, dX, R, algo, vec, per_pass / 2, g_g, g_tw, st, dZ, lambda);
-    cudaEventRecord(ev[2], st);
-    float t1 = 0.f, t2 = 0.f;
-    if (rc == FSB_OK && cudaEventSynchronize(ev[2]) == cudaSuccess) {
-      cudaEventElapsedTime(&t1, ev[0], ev[1]);
-      cudaEventElapsedTime(&t2, ev[1], ev[2]);
+    for (int k = 0; k < nc && rc == FSB_OK; ++k) {
+      rc = run_config(A, dY, dX, R, algo, vec, per_pass / cand[k].passes, g_g, g_tw, st, dZ, lambda, cand[k].deep);
+      cudaEventRecord(ev[k + 1], st);
+    }
+    if (rc == FSB_OK && cudaEventSynchronize(ev[nc]) == cudaSuccess) {
+      int best = 0;
+      for (int k = 0; k < nc; ++k) {
+        cudaEventElapsedTime(&cand[k].ms, ev[k], ev[k + 1]);
+        if (cand[k].ms < 0.97f * cand[best].ms) best = k;   // later candidates must win by 3 %
+      }
       A->tuned_R = R;
-      A->tuned_passes = (t2 < 0.97f * t1) ? 2 : 1;
+      A->tuned_passes = cand[best].passes;
+      A->tuned_deep = cand[best].deep ? 1 : 0;
     }
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;
   }
-  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st, dZ, lambda);
+  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st, dZ, lambda, A->tuned_deep != 0);
 }
 
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st) {

@@ -29,35 +29,24 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kLongRow = 2048;   // rows at least this long are split across the CTA
 
-// ---- how the U gathers of a batch are issued (compile-time experiments, tools/sweep.py + FSB_LIB):
-// FSB_STAGED_MINB  min resident CTAs per SM promised to ptxas (0 = none).  With none, ptxas budgets
-//                  32 registers per thread (full occupancy, 8 CTAs/SM) and interleaves each pair of
-//                  gathers with its adds -- about two gathers in flight per lane; with 4 it uses 54
-//                  registers and issues all U gathers back to back (SASS checked).
-// FSB_STAGED_CLAMP 1 = no control flow in the batch: indices past the row end are clamped to the
-//                  row's last entry and the value is zeroed afterwards; 0 = predicated loads.
-// Measured on C2 (profiles/r1f_sweep_c2_gather_issue.md): full occupancy with two gathers in
-// flight (MINB 0, CLAMP 0) is the fastest -- 4.8 ms against 5.35 ms for MINB 4 + CLAMP 1 -- the
-// product is bound by the random-gather throughput of L2/HBM, not by latency, and the clamped
-// form adds ~15 % L1/L2 requests.
-#ifndef FSB_STAGED_MINB
-#define FSB_STAGED_MINB 0
-#endif
-#ifndef FSB_STAGED_CLAMP
-#define FSB_STAGED_CLAMP 0
-#endif
-#if FSB_STAGED_MINB > 0
-#define FSB_STAGED_BOUNDS __launch_bounds__(kThreads, FSB_STAGED_MINB)
-#else
-#define FSB_STAGED_BOUNDS __launch_bounds__(kThreads)
-#endif
-
+// ---- two builds of the same body, chosen per matrix at run time (fsb_launch_csr_spmm times both once):
+//   LEAN  __launch_bounds__(256): ptxas budgets 32 registers (8 CTAs = 64 warps per SM) and, to fit,
+//         interleaves the gathers of a batch with their adds -- about three gathers in flight per lane;
+//   DEEP  __launch_bounds__(256, 4): 54 registers, 4 CTAs per SM, all U gathers of a batch issued
+//         back to back (an empty volatile asm after the loads pins that order; SASS checked).
+// Same box, C2 (profiles/r1f_sweep_gather_issue.md): one pass 5.63 ms either way, two column passes
+// 5.25 (lean) vs 5.10 ms (deep); power-law columns (C4) 2.98 (lean) vs 3.21 ms (deep): hot X rows
+// hit in L1/L2 and occupancy wins over depth there.  Neither saturates a unit (DRAM 62-81 %,
+// L2 51 %): the product sits on the random-gather throughput of L2 + HBM.
 #ifndef FSB_STAGED_U
 #define FSB_STAGED_U 8   // gathers per batch and lane
 #endif
+#ifndef FSB_STAGED_DEEP_MINB
+#define FSB_STAGED_DEEP_MINB 4
+#endif
 
 // Empty volatile asm that takes a loaded row piece in and out: volatile asms keep their order, so
-// placing these after the U gather asms keeps "all U loads, then the adds" in the emitted PTX.
+// placing these after the U gather asms keeps "all U loads, then the adds" in the emitted code.
 template <int VEC> __device__ __forceinline__ void pin_after_loads(double (&x)[VEC]);
 template <> __device__ __forceinline__ void pin_after_loads<1>(double (&x)[1]) { asm volatile("" : "+d"(x[0])); }
 template <> __device__ __forceinline__ void pin_after_loads<2>(double (&x)[2]) { asm volatile("" : "+d"(x[0]), "+d"(x[1])); }
@@ -66,25 +55,18 @@ template <> __device__ __forceinline__ void pin_after_loads<4>(double (&x)[4]) {
 }
 
 // One row, summed strictly in stored order, gathers issued in batches of U.
-template <int G, int VEC, bool VALS, bool FROM_SMEM>
+template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
-                                         double (&acc)[VEC], const double* __restrict__ xbase, int R,
+                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok,
                                          unsigned long long xpol) {
   constexpr int U = FSB_STAGED_U;
-  const int last = e - 1;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
     double vv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-#if FSB_STAGED_CLAMP
-      const int idx = min(i + u, last);
-      const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
-      if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
-      XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
-#else
       const int idx = i + u;
-      if (idx <= last) {
+      if (idx < e && col_ok) {
         const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
         if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
         XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
@@ -93,25 +75,15 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
 #pragma unroll
         for (int v = 0; v < VEC; ++v) xr[u][v] = 0.0;
       }
-#endif
     }
-#if FSB_STAGED_MINB > 0
+    if (DEEP) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) pin_after_loads<VEC>(xr[u]);
-#endif
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-#if FSB_STAGED_CLAMP
-      const bool ok = i + u <= last;
-#else
-      const bool ok = true;
-#endif
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const double term = ok ? xr[u][v] : 0.0;
-        acc[v] = VALS ? fma(term, vv[u], acc[v]) : acc[v] + term;
-      }
+      for (int u = 0; u < U; ++u) pin_after_loads<VEC>(xr[u]);
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = VALS ? fma(xr[u][v], vv[u], acc[v]) : acc[v] + xr[u][v];
   }
 }
 
@@ -123,11 +95,11 @@ __device__ __forceinline__ void add_scaled_row(double (&acc)[VEC], const double*
   for (int v = 0; v < VEC; ++v) acc[v] = fma(lambda, __ldg(Z + off + v), acc[v]);
 }
 
-template <int G, int VEC, bool VALS>
-__global__ void FSB_STAGED_BOUNDS
-csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
-                       const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                       int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
+template <int G, int VEC, bool VALS, bool DEEP>
+__device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                                            const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                                            int R, int col0, int ncols, int RB, int CAP, int l2mode,
+                                            const double* __restrict__ Z, double lambda) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -143,7 +115,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
   const int r0 = blockIdx.x * RB;
   const int nr = min(RB, nrow - r0);
   const bool col_ok = l * VEC < ncols;
-  const double* xbase = X + col0 + (col_ok ? l * VEC : 0);   // idle lanes (non-power-of-two widths) re-read lane 0's columns
+  const double* xbase = X + col0 + l * VEC;
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
   const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
@@ -163,7 +135,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, xpol);
+      walk_row<G, VEC, VALS, true, DEEP>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok, xpol);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -184,7 +156,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, cs, ce, acc, xbase, R, xpol);
+      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, cs, ce, acc, xbase, R, col_ok, xpol);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -204,7 +176,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false>(cols, vals, s, e, acc, xbase, R, xpol);
+      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, s, e, acc, xbase, R, col_ok, xpol);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -214,14 +186,28 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
   }
 }
 
-int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
+template <int G, int VEC, bool VALS>
+__global__ void __launch_bounds__(kThreads)
+csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                       const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                       int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
+  staged_body<G, VEC, VALS, false>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda);
+}
 
-inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+template <int G, int VEC, bool VALS>
+__global__ void __launch_bounds__(kThreads, FSB_STAGED_DEEP_MINB)
+csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                            const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                            int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
+  staged_body<G, VEC, VALS, true>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda);
+}
+
+int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 
 template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-           const double* dZ, double lambda) {
-  auto kern = csr_spmm_staged_kernel<G, VEC, VALS>;
+           const double* dZ, double lambda, bool deep) {
+  auto kern = deep ? csr_spmm_staged_deep_kernel<G, VEC, VALS> : csr_spmm_staged_kernel<G, VEC, VALS>;
   size_t body = std::max((size_t)CAP * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -232,18 +218,18 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
 
 template <int G, int VEC>
 int launch_v(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-             const double* dZ, double lambda) {
-  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda)
-                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
+             const double* dZ, double lambda, bool deep) {
+  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep)
+                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
 }
 
 template <int G>
 int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-             const double* dZ, double lambda) {
+             const double* dZ, double lambda, bool deep) {
   switch (vec) {
-    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
-    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
-    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda);
+    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
+    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
+    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
   }
 }
 
@@ -257,7 +243,7 @@ void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
 
 // one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st, const double* dZ, double lambda) {
+                               int g, int vec, cudaStream_t st, const double* dZ, double lambda, bool deep) {
   // rows per CTA: enough rows that every sub-group gets a few, bounded so that the index
   // run (~avg_nnz * RB entries) stays a small shared-memory footprint (several CTAs per SM)
   const int nt = kThreads / g;
@@ -270,12 +256,12 @@ int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX
   cap = std::max((cap + 63) & ~63, 512);
   int rc;
   switch (g) {
-    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
-    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
-    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
-    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
-    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
-    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda); break;
+    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
   }
   FSB_TRY(rc);
   FSB_KERNEL_CHECK();

@@ -392,6 +392,90 @@ def test_dense_gram_and_row_mix(R, n):
         assert np.max(np.abs(dP.cpu().numpy().reshape(n, R) - (Add + I @ M))) <= 1e-13 * scale
 
 
+def test_noise_rhs_and_sampling_step():
+    """One Macau-style sampling step with the matrix resident (bench_a_mul_b.c:334-360): device noise,
+    B = A'N + sqrt(lambda) E fused into the A' product, block-CG solve."""
+    import torch
+    L = fs.lib()
+    n = 100_003
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    fs.check(L.fsb_randn_dev(d.data_ptr(), n, 12345, None))
+    h = np.zeros(n); fs.check(L.fsb_randn_host(dp(h), n, 12345))
+    g = d.cpu().numpy()
+    assert np.max(np.abs(g - h)) < 1e-12                       # same counter-based stream on both sides
+    assert abs(g.mean()) < 0.02 and abs(g.std() - 1.0) < 0.02 and abs((g ** 3).mean()) < 0.05 and abs((g ** 4).mean() - 3.0) < 0.15
+    nrow, ncol, nnz, R, lam, seed = 50_000, 4_000, 600_000, 8, 15.0, 99
+    rows, cols, _ = fs.synth_coo_host(31337, 1, nnz, nrow, ncol)
+    A = fs.DeviceMatrix.of(fs.new_bcsr(nnz, nrow, ncol, rows, cols))
+    Bm = A.noise_rhs(R, lam, seed)
+    Nh = np.zeros(nrow * R); fs.check(L.fsb_randn_host(dp(Nh), nrow * R, seed ^ 0x9E3779B97F4A7C15))
+    Eh = np.zeros(ncol * R); fs.check(L.fsb_randn_host(dp(Eh), ncol * R, seed + 0x5bd1e995))
+    orp, occ, _ = oracle.csr_from_coo(ncol, cols, rows)        # the oracle's CSR of A'
+    want = oracle.csr_mul(ncol, orp, occ, None, Nh.reshape(nrow, R), R).reshape(-1) + np.sqrt(lam) * Eh
+    assert_close(Bm.cpu().numpy(), want, scale=4.0 * row_scale(ncol, cols) + 8.0, what="noise rhs")
+    X, it = A.cg(Bm, R, lam=lam, tol=1e-8)
+    res = (A.ata(X, R, lam=lam) - Bm).reshape(ncol, R).norm(dim=0) / Bm.reshape(ncol, R).norm(dim=0)
+    assert it > 0 and float(res.max()) < 1e-7
+    assert not torch.equal(A.noise_rhs(R, lam, seed + 1), Bm)    # a new seed is a new sample
+
+
+def _write_coo_file(path, nrow, ncol, rows, cols, vals=None):
+    """The reference's raw COO format (sparse.h:112-139, dsparse.h:64-93): 3 x int64, 1-based int32 indices."""
+    with open(path, "wb") as f:
+        np.array([nrow, ncol, rows.size], dtype=np.int64).tofile(f)
+        (rows + 1).astype(np.int32).tofile(f)
+        (cols + 1).astype(np.int32).tofile(f)
+        if vals is not None:
+            vals.astype(np.float64).tofile(f)
+
+
+def test_file_loaders_straight_to_hbm(tmp_path):
+    """read_sbm / read_sdm / .csr.bin files loaded directly into HBM (chunked, pinned staging) give the
+    same structure, bit for bit, as the host loaders + new_bcsr / new_csr (csr.h:30-67, 375-422)."""
+    for name, with_vals in (("sbm-100-50.data", False), ("sdm-100-50.data", True)):
+        path = os.path.join(DATA, name)
+        M = fs.DeviceMatrix.load_coo_file(path, with_vals)
+        H = fs.read_sdm(path) if with_vals else fs.read_sbm(path)
+        want = fs.new_csr(H.nnz, H.nrow, H.ncol, H.rows, H.cols, H.vals) if with_vals else fs.new_bcsr(H.nnz, H.nrow, H.ncol, H.rows, H.cols)
+        rp, cc, vv = M.download_csr()
+        assert (M.nrow, M.ncol, M.nnz) == (H.nrow, H.ncol, H.nnz)
+        assert np.array_equal(rp, want.row_ptr) and np.array_equal(cc, want.cols)
+        assert (vv is None) == (not with_vals) and (vv is None or np.array_equal(vv, want.vals))
+    # several staging chunks per array (5M entries = 20 MB of indices, 40 MB of values), duplicates, empty rows
+    rng = np.random.default_rng(77)
+    nrow, ncol, nnz = 300_000, 70_000, 5_000_000
+    rows = rng.integers(0, nrow // 2, nnz).astype(np.int32) * 2     # odd rows stay empty
+    cols = rng.integers(0, ncol, nnz).astype(np.int32)
+    vals = rng.standard_normal(nnz)
+    for with_vals in (False, True):
+        path = str(tmp_path / ("big.sdm" if with_vals else "big.sbm"))
+        _write_coo_file(path, nrow, ncol, rows, cols, vals if with_vals else None)
+        M = fs.DeviceMatrix.load_coo_file(path, with_vals)
+        orp, occ, ovv = oracle.csr_from_coo(nrow, rows, cols, vals if with_vals else None)
+        rp, cc, vv = M.download_csr()
+        assert np.array_equal(rp, orp) and np.array_equal(cc, occ) and (not with_vals or np.array_equal(vv, ovv))
+    # .csr.bin written by serialize_to_file, read back into HBM
+    B = fs.new_bcsr(nnz, nrow, ncol, rows, cols)
+    path = str(tmp_path / "big.csr.bin")
+    fs.serialize_to_file(B, path)
+    M = fs.DeviceMatrix.load_csr_bin(path)
+    rp, cc, _ = M.download_csr()
+    assert (M.nrow, M.ncol, M.nnz) == (nrow, ncol, nnz) and np.array_equal(rp, B.row_ptr) and np.array_equal(cc, B.cols)
+    x = tvec(ncol); y = np.zeros(nrow); fs.bcsr_A_mul_B(y, B, x)
+    import torch
+    yd = M.spmm(torch.from_numpy(x).cuda(), 1).cpu().numpy()
+    assert np.max(np.abs(yd - y)) <= 1e-12 * row_scale(nrow, rows)
+    # error behaviour: truncated and foreign files are rejected
+    bad = str(tmp_path / "bad.csr.bin")
+    open(bad, "wb").write(open(path, "rb").read()[:1000])
+    with pytest.raises(fs.FsbError):
+        fs.DeviceMatrix.load_csr_bin(bad)
+    with pytest.raises(fs.FsbError):
+        fs.DeviceMatrix.load_csr_bin(os.path.join(DATA, "sbm-100-50.data"))
+    with pytest.raises(fs.FsbError):
+        fs.DeviceMatrix.load_coo_file(str(tmp_path / "missing.data"))
+
+
 # ------------------------------------------------------------------ BASELINE.json full size: size-independent properties
 def test_full_size_c2_properties():
     """C2: binary CSR 10M x 1M, 200M nnz, R = 32.  Checks: (i) a slab of rows against the oracle,

@@ -140,6 +140,7 @@ def main():
         E = torch.randn(F * R, dtype=torch.float64, device="cuda", generator=g)
         Bm = M.spmm_t(Nn, R) + (15.0 ** 0.5) * E          # B = A'N + sqrt(lambda) E   (bench_a_mul_b.c:334-347)
         del Nn, E
+        M.cg(Bm, R, lam=15.0, tol=1e-30, max_iter=2)     # warm-up: per-handle autotune of A (A' was tuned by spmm_t above)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         Xs, it = M.cg(Bm, R, lam=15.0, tol=1e-6)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0

@@ -78,16 +78,20 @@ def main():
     E = torch.randn(F * R, dtype=torch.float64, device="cuda", generator=g)
     Bm = A.spmm_t(Nn[r0 * R: r1 * R].contiguous(), R) + (15.0 ** 0.5) * E     # allreduced inside: B = A'N + sqrt(lambda) E
     del Nn, E
-    Xs, it = A.cg(Bm, R, lam=15.0, tol=1e-6)          # warm-up (builds the cached transpose)
-    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    Xs, it = A.cg(Bm, R, lam=15.0, tol=1e-6)
-    dist.barrier(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-    res = (A.ata(Xs, R, lam=15.0) - Bm).reshape(F, R).norm(dim=0) / Bm.reshape(F, R).norm(dim=0)
-    per_it = dt / (it + 1)
-    out.append(dict(config="C5 block CG R=32 lambda=15 tol=1e-6, row-sharded A, NCCL allreduce of [F][32] per iteration", n_gpus=world,
-                    iterations=it, seconds=dt, ms_per_iteration=per_it * 1e3, nnz_rhs_per_s=2 * NNZ * R / per_it, max_rel_residual=float(res.max()),
-                    scaling="strong"))
+    for mode, name in ((0, "vectors sharded over F: reduce-scatter (overlapped) + all-gather of P + R x R Gram allreduce"),
+                       (1, "vectors replicated: allreduce of the [F][32] partial")):
+        fs.check(fs.lib().fsb_tune_cg_dist(mode))
+        Xs, it = A.cg(Bm, R, lam=15.0, tol=1e-6)          # warm-up (builds the cached transpose)
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        Xs, it = A.cg(Bm, R, lam=15.0, tol=1e-6)
+        dist.barrier(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        res = (A.ata(Xs, R, lam=15.0) - Bm).reshape(F, R).norm(dim=0) / Bm.reshape(F, R).norm(dim=0)
+        per_it = dt / (it + 1)
+        out.append(dict(config="C5 block CG R=32 lambda=15 tol=1e-6, row-sharded A; " + name, n_gpus=world,
+                        iterations=it, seconds=dt, ms_per_iteration=per_it * 1e3, nnz_rhs_per_s=2 * NNZ * R / per_it, max_rel_residual=float(res.max()),
+                        scaling="strong"))
+    fs.check(fs.lib().fsb_tune_cg_dist(0))
     ms = timed(lambda: A.ata(Xs, R, lam=15.0), 5)
     out.append(dict(config="C5 operator A'(A X)+lambda X, R=32, row-sharded + allreduce", n_gpus=world, ms=ms, nnz_rhs_per_s=2 * NNZ * R / ms * 1e3, scaling="strong"))
     if rank == 0:

@@ -56,10 +56,18 @@ def main():
             out[f"{tag}_AtA_mode{mode}_err"] = float((Ks - K).abs().max() / K.abs().max())
         # block CG on the shard vs on the full matrix
         Xf, itf = full.cg(B, R, lam=15.0, tol=1e-8)
-        Xs, its = shard.cg(B, R, lam=15.0, tol=1e-8)
-        out[tag + "_cg_iters"] = [itf, its]
-        out[tag + "_cg_err"] = float((Xs - Xf).abs().max() / Xf.abs().max())
-        ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12 and out[tag + "_cg_err"] < 1e-6 and abs(itf - its) <= max(2, itf // 20)
+        ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12
+        for mode, name in ((0, "sharded"), (1, "replicated")):   # CG vectors sharded over the unknowns / replicated
+            fs.check(fs.lib().fsb_tune_cg_dist(mode))
+            Xs, its = shard.cg(B, R, lam=15.0, tol=1e-8)
+            out[f"{tag}_cg_{name}_iters"] = [itf, its]
+            out[f"{tag}_cg_{name}_err"] = float((Xs - Xf).abs().max() / Xf.abs().max())
+            ok &= out[f"{tag}_cg_{name}_err"] < 1e-6 and abs(itf - its) <= max(2, itf // 20)
+            lo = Xs.sum().reshape(1).clone(); hi = lo.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            out[f"{tag}_cg_{name}_ranks_agree"] = bool(lo.item() == hi.item())
+            ok &= out[f"{tag}_cg_{name}_ranks_agree"]
+        fs.check(fs.lib().fsb_tune_cg_dist(0))
         ok &= all(out[f"{tag}_AtA_mode{m}_err"] < 1e-12 for m in (0, 1))
         # all ranks must hold the same allreduced result
         chk = Zs.sum().reshape(1).clone(); lo = chk.clone(); hi = chk.clone()

@@ -35,13 +35,25 @@ def main():
         R = args.R
     if args.dist >= 0:
         dkind = args.dist
+    # box calibration: plain device copy bandwidth (read + write bytes), to compare runs on different boxes
+    a = torch.empty(1 << 28, dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    for _ in range(3):
+        b.copy_(a)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(10):
+        b.copy_(a)
+    c1.record(); torch.cuda.synchronize()
+    print(json.dumps({"calibration_copy_gbs": 2 * a.numel() * 4 * 10 / (c0.elapsed_time(c1) * 1e-3) / 1e9}), flush=True)
+    del a, b
     A = fs.DeviceMatrix.synth(seed, dkind, nnz, nrow, ncol, with_vals=args.vals)
     nin, nout = (nrow, ncol) if args.transpose else (ncol, nrow)
     X = torch.randn(nin * R, dtype=torch.float64, device="cuda")
     Y = torch.empty(nout * R, dtype=torch.float64, device="cuda")
     run = (lambda: A.spmm_t(X, R, out=Y)) if args.transpose else (lambda: A.spmm(X, R, out=Y))
     if args.combos:
-        combos = [tuple(int(v) for v in c.split(",")) for c in args.combos.split(";")]
+        combos = [tuple(int(v) for v in c.split(",")) for c in args.combos.split(";")]   # optional 7th value: staged build (0 lean, 1 deep)
     else:
         combos = [(0, 0, 0, 0, 0, 0)]
         for vec in (4, 2, 1):
@@ -57,7 +69,10 @@ def main():
                     combos.append((1, tw, g, vec, 1, 0))
     ref = None
     rows = []
-    for algo, tw, g, vec, slabs, rb in combos:
+    for combo in combos:
+        algo, tw, g, vec, slabs, rb = combo[:6]
+        deep = combo[6] if len(combo) > 6 else -1
+        fs.check(fs.lib().fsb_tune_csr_staged(deep))
         fs.check(fs.lib().fsb_tune_csr_algo(algo, rb, 0))
         fs.check(fs.lib().fsb_tune_csr_spmm(tw, g, vec, slabs))
         for _ in range(2):
@@ -78,7 +93,7 @@ def main():
         idx_bytes = 12 if args.vals else 4
         ab = nnz * (idx_bytes + 8 * R) + 4 * (nout + 1) + 8 * nout * R if 8 * nin * R > 126e6 else \
             nnz * idx_bytes + 4 * (nout + 1) + 8 * nout * R + 8 * nin * R
-        row = dict(algo=algo, tw=tw, g=g, vec=vec, slabs=slabs, rb=rb, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=ab / ms / 1e6, maxdiff=err)
+        row = dict(algo=algo, tw=tw, g=g, vec=vec, slabs=slabs, rb=rb, deep=deep, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=ab / ms / 1e6, maxdiff=err)
         rows.append(row)
         print(json.dumps(row), flush=True)
     if args.out:
