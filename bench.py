@@ -205,6 +205,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = fs.launch_count() - l0
+    tuned = A.tuning()
     clocks = sampler.stop() if sampler else None
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
@@ -251,9 +252,12 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: binary CSR {nrow}x{ncol}, {nnz} nnz per GPU, A_mul_Bn R={R} (bcsr_A_mul_Bn / _B32n)",
                        "parallelism": f"row-sharded x{world}, X replicated, no collective", "l2": "inputs larger than L2 (no flush)",
-                       "x_pattern": "sin(7c+17k+0.3)", "tune": args.tune or "auto"},
+                       "x_pattern": "sin(7c+17k+0.3)", "tune": args.tune or "auto",
+                       "kernel": "csr_spmm_staged%s_kernel, %d column pass(es) per step" % ("_deep" if tuned[2] else "", tuned[1])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "alg_bytes_per_launch": ab, "peak_source": peak_src,
+                         "traffic": traffic, "alg_bytes_per_launch": ab, "launches_per_step": tuned[1],
+                         "note": "achieved = algorithmic bytes of one product / time of one product (all its column-pass launches); "
+                                 "traffic = ncu dram bytes of one product (profiles/c2_spmm_traffic.json)", "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "nnz*RHS/s", "h2d_bytes_per_step": ncol * R * 8, "d2h_bytes_per_step": nrow * R * 8,
                     "ms_per_step": e2e_s * 1e3, "api": "fsb_spmm_host (bcsr_A_mul_Bn drop-in path), pinned host buffers",

@@ -87,6 +87,9 @@ int fsb_matrix_info(fsb_matrix_t A, int* format, int* nrow, int* ncol, long* nnz
                     int* has_vals, int* nblocks);
 /* bytes of HBM held by the handle (structure + cached transposes) */
 long fsb_matrix_bytes(fsb_matrix_t A);
+/* the staged SpMM's per-handle autotune result (transposed != 0: of the cached transpose):
+ * *R = width it was timed for (0 = not yet), *passes = column passes (1 | 2), *deep = kernel build */
+int fsb_matrix_tuning(fsb_matrix_t A, int transposed, int* R, int* passes, int* deep);
 /* row-blocked COO built on the device from a device COO; order 0 = COO order kept
  * (new_bsbm), 1 = per-block Hilbert order (new_bsbm + sort_bsbm sparse.h:215-236),
  * 2 = per-block row-major order (sort_bsbm_byrow sparse.h:238-256) */

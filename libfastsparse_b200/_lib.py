@@ -44,6 +44,7 @@ _SIGS = {
     "fsb_matrix_free": (C.c_int, [handle]),
     "fsb_matrix_info": (C.c_int, [handle, c_int_p, c_int_p, c_int_p, c_long_p, c_int_p, c_int_p]),
     "fsb_matrix_bytes": (C.c_long, [handle]),
+    "fsb_matrix_tuning": (C.c_int, [handle, C.c_int, c_int_p, c_int_p, c_int_p]),
     "fsb_csr_download": (C.c_int, [handle, c_int_p, c_int_p, c_dbl_p]),
     "fsb_csr_row_slice": (C.c_int, [C.POINTER(handle), handle, C.c_int, C.c_int]),
     "fsb_spmm_dev": (C.c_int, [handle, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

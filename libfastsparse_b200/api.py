@@ -654,6 +654,12 @@ class DeviceMatrix:
     def bytes(self):
         return lib().fsb_matrix_bytes(self.h)
 
+    def tuning(self, transposed=False):
+        """(R, column passes, deep build) chosen by the staged SpMM's per-handle autotune; R = 0 before the first product."""
+        R, p, d = C.c_int(), C.c_int(), C.c_int()
+        check(lib().fsb_matrix_tuning(self.h, int(transposed), C.byref(R), C.byref(p), C.byref(d)))
+        return R.value, p.value, bool(d.value)
+
     def spmm(self, dX, R, out=None):
         import torch
         if out is None:

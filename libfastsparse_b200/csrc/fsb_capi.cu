@@ -121,6 +121,8 @@ int fsb_matrix_carry(fsb_matrix* A, size_t bytes, double** out) {
 
 static void free_arrays(fsb_matrix* A) {
   if (!A) return;
+  if (A->cg_cache && A->cg_cache_free) A->cg_cache_free(A->cg_cache);
+  A->cg_cache = nullptr;
   cudaFree(A->carry);
   cudaFree(A->split);
   cudaFree(A->row_ptr); cudaFree(A->cols); cudaFree(A->vals);
@@ -249,6 +251,18 @@ int fsb_matrix_info(fsb_matrix_t A, int* format, int* nrow, int* ncol, long* nnz
   if (nnz) *nnz = A->nnz;
   if (has_vals) *has_vals = A->has_vals;
   if (nblocks) *nblocks = A->nblocks;
+  return FSB_OK;
+}
+
+// what the per-handle autotune of the staged SpMM settled on (see fsb_launch_csr_spmm):
+// *R = the width it was timed for (0 = not tuned yet), *passes = column passes, *deep = kernel build
+int fsb_matrix_tuning(fsb_matrix_t A, int transposed, int* R, int* passes, int* deep) {
+  if (!A) return fsb_set_error(FSB_EINVAL, "fsb_matrix_tuning: null handle");
+  const fsb_matrix* M = A->format == FSB_FMT_CSR ? A : A->view;
+  if (transposed) M = A->T;
+  if (R) *R = M ? M->tuned_R : 0;
+  if (passes) *passes = M ? M->tuned_passes : 1;
+  if (deep) *deep = M ? M->tuned_deep : 0;
   return FSB_OK;
 }
 

@@ -280,6 +280,8 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   const int batch = work >= 2e8 ? 1 : 4;
   int queued = 0, np = 0;
   w.h_status[0] = w.h_status[1] = w.h_status[2] = 0;
+  double t_prev = 0.0;
+  if (cg_trace()) { cudaStreamSynchronize(st); t_prev = now_ms(); }
   while (queued < max_iter) {
     const int nb = std::min(batch, max_iter - queued);
     for (int k = 0; k < nb; ++k) {
@@ -298,6 +300,12 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
     queued += nb;
     FSB_CUDA(cudaMemcpyAsync(w.h_status, w.status, kStatusWords * sizeof(int), cudaMemcpyDeviceToHost, st));
     FSB_CUDA(cudaStreamSynchronize(st));
+    if (cg_trace()) {
+      const double t = now_ms();
+      fprintf(stderr, "[fsb cg %d/%d] iterations %d..%d: %.3f ms (status %d %d %d)\n", w.rank, w.G, queued - nb, queued - 1, t - t_prev,
+              w.h_status[0], w.h_status[1], w.h_status[2]);
+      t_prev = t;
+    }
     if (w.h_status[0] || w.h_status[1]) break;
   }
   const int it = w.h_status[2];
@@ -314,27 +322,49 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
 
 int g_cg_dist_mode = 0;   // 0 = sharded vectors when a communicator is active, 1 = replicated vectors + allreduce
 
+// The workspace of a solve (a few [F][R] vectors and the [N][R] intermediate: 3.6 GB at C5) stays
+// with the handle between solves -- a sampler calls the solver thousands of times on one matrix, and
+// cudaMalloc / cudaFree of gigabytes cost ~10 ms per solve (more with NCCL buffers registered).
+struct CgCache {
+  int kind = 0, R = 0, G = 1;
+  long F = 0, N = 0;
+  CgWork w;
+  CgShardWork sw;
+};
+void cg_cache_free(void* p) {
+  CgCache* c = static_cast<CgCache*>(p);
+  if (!c) return;
+  c->w.release();
+  c->sw.release();
+  delete c;
+}
+
 // one solve through whichever path applies to the handle
 int cg_solve(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, double lambda, double tol, int max_iter,
              int* out_iter, cudaStream_t st) {
   const bool shard = A->sharded && fsb_comm_active() && g_cg_dist_mode == 0 && (long)A->ncol >= 64L * fsb_comm_size();
+  const int kind = shard ? 2 : 1, G = shard ? fsb_comm_size() : 1;
+  const double t0 = cg_trace() ? now_ms() : 0.0;
+  CgCache* c = static_cast<CgCache*>(A->cg_cache);
+  if (!c || c->kind != kind || c->R != R || c->F != A->ncol || c->N != A->nrow || c->G != G) {
+    if (c) cg_cache_free(c);
+    A->cg_cache = nullptr;
+    c = new CgCache();
+    c->kind = kind; c->R = R; c->G = G; c->F = A->ncol; c->N = A->nrow;
+    const int rc = shard ? shard_alloc(c->sw, A->ncol, A->nrow, R) : cg_alloc(c->w, A->ncol, A->nrow, R);
+    if (rc != FSB_OK) { cg_cache_free(c); return rc; }
+    A->cg_cache = c;
+    A->cg_cache_free = cg_cache_free;
+  }
+  const double t1 = cg_trace() ? now_ms() : 0.0;
   int rc;
   if (shard) {
-    CgShardWork w;
-    rc = shard_alloc(w, A->ncol, A->nrow, R);
-    if (rc == FSB_OK) rc = cg_run_sharded(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, w);
-    cudaStreamSynchronize(w.comm_st ? w.comm_st : st);
-    w.release();
+    rc = cg_run_sharded(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, c->sw);
+    cudaStreamSynchronize(c->sw.comm_st);
   } else {
-    CgWork w;
-    const double t0 = cg_trace() ? now_ms() : 0.0;
-    rc = cg_alloc(w, A->ncol, A->nrow, R);
-    const double t1 = cg_trace() ? now_ms() : 0.0;
-    if (rc == FSB_OK) rc = cg_run(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, w);
-    const double t2 = cg_trace() ? now_ms() : 0.0;
-    w.release();
-    if (cg_trace()) fprintf(stderr, "[fsb cg] alloc %.3f ms, solve %.3f ms, release %.3f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
+    rc = cg_run(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, st, c->w);
   }
+  if (cg_trace()) fprintf(stderr, "[fsb cg] workspace %.3f ms, solve %.3f ms (%s)\n", t1 - t0, now_ms() - t1, shard ? "sharded vectors" : "replicated vectors");
   return rc;
 }
 

@@ -45,6 +45,9 @@ struct fsb_matrix {
   int tuned_deep = 0;         //   lean (0) or deep (1) build of the kernel
   size_t bytes = 0;
   double avg_row_nnz = 0.0;
+  // solver workspace kept between solves on this handle (fsb_cg.cu); released with the handle
+  void* cg_cache = nullptr;
+  void (*cg_cache_free)(void*) = nullptr;
 };
 
 // ---- error plumbing (fsb_runtime.cu)

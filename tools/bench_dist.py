@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="", help="c3 | c5")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -59,7 +60,18 @@ def main():
         return sh, r0, r1
 
     out = []
-    # ---- C3
+    if args.only in ("", "c3"):
+        bench_c3(args, world, NNZ, N, F, shard_of, timed, out)
+    if args.only in ("", "c5"):
+        bench_c5(args, world, rank, NNZ, N, F, shard_of, timed, out)
+    if rank == 0:
+        for o in out:
+            print(json.dumps(o), flush=True)
+    fs.comm_finalize()
+    dist.destroy_process_group()
+
+
+def bench_c3(args, world, NNZ, N, F, shard_of, timed, out):
     A, r0, r1 = shard_of(0x5EED0003, True)
     x = (torch.sin(7.0 * torch.arange(F, device="cuda", dtype=torch.float64) + 0.3) / 10).contiguous()
     y = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
@@ -70,7 +82,9 @@ def main():
     ms = timed(lambda: A.spmm_t(y, 1, out=z), args.reps)
     out.append(dict(config="C3 double CSR At_mul_B, row-sharded, NCCL allreduce of [F]", n_gpus=world, ms=ms, nnz_per_s=NNZ / ms * 1e3, scaling="strong"))
     A.free(); del A, x, y, z
-    # ---- C5
+
+
+def bench_c5(args, world, rank, NNZ, N, F, shard_of, timed, out):
     R = 32
     A, r0, r1 = shard_of(0x5EED0002, False)
     g = torch.Generator(device="cuda"); g.manual_seed(5)
@@ -94,11 +108,6 @@ def main():
     fs.check(fs.lib().fsb_tune_cg_dist(0))
     ms = timed(lambda: A.ata(Xs, R, lam=15.0), 5)
     out.append(dict(config="C5 operator A'(A X)+lambda X, R=32, row-sharded + allreduce", n_gpus=world, ms=ms, nnz_rhs_per_s=2 * NNZ * R / ms * 1e3, scaling="strong"))
-    if rank == 0:
-        for o in out:
-            print(json.dumps(o), flush=True)
-    fs.comm_finalize()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
