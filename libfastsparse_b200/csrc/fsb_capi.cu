@@ -422,9 +422,9 @@ int fsb_noise_rhs_dev(fsb_matrix_t A, fsb_matrix_t At, double* dB, int R, double
     return fsb_set_error(FSB_EINVAL, "A (%d x %d) and At (%d x %d) must be transposes of each other.", A->nrow, A->ncol, At->nrow, At->ncol);
   cudaStream_t st = fsb_pick_stream(stream);
   const long nN = (long)A->nrow * R, nF = (long)A->ncol * R;
-  double *dN = nullptr, *dE = nullptr;
-  FSB_TRY(fsb_matrix_scratch(A, (size_t)std::max(nN, 1L) * sizeof(double), &dN));
-  FSB_CUDA(cudaMalloc(&dE, (size_t)std::max(nF, 1L) * sizeof(double)));
+  double *dN = nullptr, *dE = nullptr;   // both in the handle's scratch buffer: nothing is allocated per sample
+  FSB_TRY(fsb_matrix_scratch(A, (size_t)std::max(nN + nF, 1L) * sizeof(double), &dN));
+  dE = dN + nN;
   // every rank of a row-sharded solve draws its own N rows (seed offset by the rank) and the same E
   const unsigned long long nseed = seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(A->sharded ? fsb_comm_rank() + 1 : 1));
   int rc = fsb_randn_dev(dN, nN, nseed, (void*)st);
@@ -443,9 +443,6 @@ int fsb_noise_rhs_dev(fsb_matrix_t A, fsb_matrix_t At, double* dB, int R, double
       }
     }
   }
-  cudaError_t e = cudaStreamSynchronize(st);   // dE is released below
-  cudaFree(dE);
-  if (rc == FSB_OK && e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_noise_rhs_dev", __FILE__, __LINE__);
   return rc;
 }
 
