@@ -392,6 +392,37 @@ def test_dense_gram_and_row_mix(R, n):
         assert np.max(np.abs(dP.cpu().numpy().reshape(n, R) - (Add + I @ M))) <= 1e-13 * scale
 
 
+@pytest.mark.parametrize("with_vals", [False, True])
+def test_staged_builds_and_column_passes_agree_bitwise(with_vals):
+    """The per-handle autotune of the staged SpMM picks between column passes (1 | 2) and the lean / deep
+    build of the kernel by timing: every candidate must give the same bits (each column's sum is taken in
+    stored order), and the choice it records must be one of them."""
+    import torch
+    L = fs.lib()
+    nrow, ncol, nnz, R = 400_000, 120_000, 6_000_000, 32       # >= 4M entries: the autotune engages
+    A = fs.DeviceMatrix.synth(0xABCD, 1, nnz, nrow, ncol, with_vals=with_vals)
+    X = torch.randn(ncol * R, dtype=torch.float64, device="cuda")
+    ref = None
+    try:
+        for slabs in (1, 2):
+            for deep in (0, 1):
+                fs.check(L.fsb_tune_csr_algo(2, 0, 0)); fs.check(L.fsb_tune_csr_spmm(0, 0, 0, slabs)); fs.check(L.fsb_tune_csr_staged(deep))
+                Y = A.spmm(X, R)
+                ref = Y if ref is None else ref
+                assert torch.equal(Y, ref), f"slabs={slabs} deep={deep} differs"
+    finally:
+        fs.check(L.fsb_tune_csr_algo(0, 0, 0)); fs.check(L.fsb_tune_csr_spmm(0, 0, 0, 0)); fs.check(L.fsb_tune_csr_staged(-1))
+    assert A.tuning()[0] == 0                                   # explicit settings do not touch the recorded choice
+    Y = A.spmm(X, R)                                            # first automatic product: times the candidates
+    tR, passes, deep = A.tuning()
+    assert tR == R and passes in (1, 2) and torch.equal(Y, ref)
+    assert torch.equal(A.spmm(X, R), ref)                       # steady state uses the recorded choice
+    # the fused epilogue Y = A X + lambda Z agrees with the two-step form to rounding of one fma
+    K = A.ata(X, R, lam=0.75)                                   # A'(A X) + 0.75 X through the fused epilogue
+    K2 = A.spmm_t(ref, R) + 0.75 * X
+    assert float((K - K2).abs().max()) <= 1e-12 * float(K2.abs().max())
+
+
 def test_noise_rhs_and_sampling_step():
     """One Macau-style sampling step with the matrix resident (bench_a_mul_b.c:334-360): device noise,
     B = A'N + sqrt(lambda) E fused into the A' product, block-CG solve."""
