@@ -239,11 +239,11 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         ab = alg_bytes(nrow, nnz, R)
         achieved = ab / (ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None      # ncu DRAM bytes of one product in the configuration this run used (column passes)
         tp = os.path.join(ROOT, "profiles", "c2_spmm_traffic.json")
-        if os.path.exists(tp):
+        if args.workload == "c2" and os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp))["by_column_passes"][str(tuned[1])]["dram_bytes_per_product"]
             except Exception:
                 traffic = None
         line = {
@@ -255,9 +255,12 @@ def run_ours(args):
                        "x_pattern": "sin(7c+17k+0.3)", "tune": args.tune or "auto",
                        "kernel": "csr_spmm_staged%s_kernel, %d column pass(es) per step" % ("_deep" if tuned[2] else "", tuned[1])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "alg_bytes_per_launch": ab, "launches_per_step": tuned[1],
+                         "traffic": traffic, "dram_gbs": (traffic / (ms * 1e-3) / 1e9) if traffic else None,
+                         "dram_frac": (traffic / (ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "alg_bytes_per_launch": ab, "launches_per_step": tuned[1],
                          "note": "achieved = algorithmic bytes of one product / time of one product (all its column-pass launches); "
-                                 "traffic = ncu dram bytes of one product (profiles/c2_spmm_traffic.json)", "peak_source": peak_src,
+                                 "traffic = ncu dram bytes of one product (profiles/c2_spmm_traffic.json), dram_gbs / dram_frac = that traffic / this run's time (frac > 1 on the "
+                                 "algorithmic count means L2 served part of the X gathers, not that work was skipped)", "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "nnz*RHS/s", "h2d_bytes_per_step": ncol * R * 8, "d2h_bytes_per_step": nrow * R * 8,
                     "ms_per_step": e2e_s * 1e3, "api": "fsb_spmm_host (bcsr_A_mul_Bn drop-in path), pinned host buffers",

@@ -188,6 +188,11 @@ int fsb_comm_size(void);
 int fsb_comm_rank(void);
 int fsb_allreduce_sum_dev(double* dBuf, long count, void* stream);
 int fsb_matrix_set_row_sharded(fsb_matrix_t A, int sharded);
+/* geometry of the multi-GPU block CG's F-sharded vectors on G ranks: the F unknowns are cut into *C chunks of
+ * *Fc = G * *s rows (zero-padded to *Fp = *C * *Fc); rank g owns rows [c * *Fc + g * *s, + *s) of every chunk c,
+ * stored back to back (*nloc = *C * *s local rows).  Chunk c of the A'(A P) partial is reduce-scattered while
+ * chunk c+1 is computed; P is all-gathered chunk by chunk.  Pure host arithmetic (no device needed). */
+int fsb_cg_shard_layout(long F, int R, int G, int* C, long* s, long* Fc, long* Fp, long* nloc);
 /* nnz-balanced contiguous row partition: bounds[p]..bounds[p+1] are the rows of
  * part p, chosen from row_ptr so each part holds ~nnz/nparts entries.  Host only. */
 int fsb_partition_rows(int nrow, const int* row_ptr, int nparts, int* bounds);

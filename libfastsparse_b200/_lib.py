@@ -64,6 +64,7 @@ _SIGS = {
     "fsb_rowmix_dev": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_dbl_p, C.c_long, C.c_int, C.c_void_p]),
     "fsb_dist_host": (C.c_int, [c_dbl_p, c_dbl_p, c_dbl_p, C.c_long]),
     "fsb_ata_pair_host": (C.c_int, [handle, handle, c_dbl_p, c_dbl_p, C.c_int, C.c_double, c_dbl_p]),
+    "fsb_cg_shard_layout": (C.c_int, [C.c_long, C.c_int, C.c_int, c_int_p, c_long_p, c_long_p, c_long_p, c_long_p]),
     "fsb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "fsb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "fsb_comm_finalize": (C.c_int, []),

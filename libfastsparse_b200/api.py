@@ -27,7 +27,7 @@ __all__ = [
     "new_cbcsr", "cbcsr_from_sbm", "cbcsr_A_mul_B", "cbcsr_A_mul_Bn", "bsbm_AtA", "bsbm_cg", "bsbm_cg2", "bsbm_cgn",
     "pnormsq", "pnormsq2", "pouter2", "pdot", "pdot2sym", "solve2sym", "dist", "ceilPower2", "xy2d", "d2xy", "row_xy2d",
     "row_d2xy", "quickSort", "quickSortD", "partition_rows", "synth_coo_host", "device_count", "launch_count",
-    "comm_init_from_torch", "comm_finalize", "allreduce_sum",
+    "comm_init_from_torch", "comm_finalize", "allreduce_sum", "cg_shard_layout",
 ]
 
 
@@ -726,6 +726,13 @@ def comm_init_from_torch():
     raw = bytes(t.cpu().tolist())
     check(lib().fsb_comm_init(world, rank, raw))
     return world, rank
+
+
+def cg_shard_layout(F, R, G):
+    """(C, s, Fc, Fp, nloc): chunk / slice geometry of the multi-GPU block CG's F-sharded vectors (fsb.h)."""
+    Cc = C.c_int(); s, Fc, Fp, nloc = C.c_long(), C.c_long(), C.c_long(), C.c_long()
+    check(lib().fsb_cg_shard_layout(int(F), int(R), int(G), C.byref(Cc), C.byref(s), C.byref(Fc), C.byref(Fp), C.byref(nloc)))
+    return Cc.value, s.value, Fc.value, Fp.value, nloc.value
 
 
 def comm_finalize():

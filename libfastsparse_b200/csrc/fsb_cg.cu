@@ -170,14 +170,19 @@ struct CgShardWork {
   }
 };
 
-int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
-  w.G = fsb_comm_size(); w.rank = fsb_comm_rank(); w.F = F;
+// chunk / slice geometry of the F-sharded vectors on G ranks (also exported for the CPU tests of the exchange pattern)
+void shard_layout(long F, int R, int G, int* C, long* s, long* Fc, long* Fp, long* nloc) {
   // chunks only pay off when a chunk is a sizeable transfer; R = 1 keeps one chunk (its products may
   // take the merge-path kernel, which caches per-handle state and must see the whole matrix)
-  w.C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? kMaxChunks : 1;
-  w.s = (F + (long)w.C * w.G - 1) / ((long)w.C * w.G);
-  if ((w.s * R) % 2) w.s += 1;            // keep every slice 16-byte aligned for the vector paths
-  w.Fc = w.s * w.G; w.Fp = w.Fc * w.C; w.nloc = w.s * w.C;
+  *C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? kMaxChunks : 1;
+  *s = (F + (long)*C * G - 1) / ((long)*C * G);
+  if ((*s * R) % 2) *s += 1;            // keep every slice 16-byte aligned for the vector paths
+  *Fc = *s * G; *Fp = *Fc * *C; *nloc = *s * *C;
+}
+
+int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
+  w.G = fsb_comm_size(); w.rank = fsb_comm_rank(); w.F = F;
+  shard_layout(F, R, w.G, &w.C, &w.s, &w.Fc, &w.Fp, &w.nloc);
   const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8, rr = (size_t)R * R * 8;
   FSB_CUDA(cudaMalloc(&w.Pfull, full)); FSB_CUDA(cudaMalloc(&w.KPpart, full));
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
@@ -369,6 +374,12 @@ int cg_solve(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R,
 }
 
 }  // namespace
+
+extern "C" int fsb_cg_shard_layout(long F, int R, int G, int* C, long* s, long* Fc, long* Fp, long* nloc) {
+  if (F < 0 || R < 1 || G < 1 || !C || !s || !Fc || !Fp || !nloc) return fsb_set_error(FSB_EINVAL, "fsb_cg_shard_layout: bad arguments");
+  shard_layout(F, R, G, C, s, Fc, Fp, nloc);
+  return FSB_OK;
+}
 
 extern "C" int fsb_tune_cg_dist(int mode) {
   if (mode < 0 || mode > 1) return fsb_set_error(FSB_EINVAL, "fsb_tune_cg_dist: mode must be 0 (sharded vectors) or 1 (replicated)");
