@@ -164,26 +164,34 @@ gram_partial_kernel(double* __restrict__ partial, const double* Xa, const double
   reduce_gram_cta<NB, V32, SYM>(red, acc, partial, R);
 }
 
-// element e of the sum of nparts partial Gram matrices: eight interleaved running sums (eight
-// loads in flight instead of a dependent chain), combined in a fixed tree => deterministic
-__device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int nparts, int RR, int e) {
-  double s[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s[k] = 0.0;
-  int p = 0;
-  for (; p + 8 <= nparts; p += 8)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s[k] += partial[(size_t)(p + k) * RR + e];
-  for (int k = 0; p < nparts; ++p, ++k) s[k] += partial[(size_t)p * RR + e];
-  return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+// G[e] = sum over the partial Gram matrices, second stage of the reductions above.  A CTA owns 32
+// consecutive elements; its eight warps each sum every eighth partial (four interleaved running sums:
+// four loads in flight per thread) and are combined through shared memory in a fixed tree, so the
+// result does not depend on scheduling.  (A first version with one thread per element and 4 CTAs
+// took 130 us cold: a chain of ~300 dependent loads per thread.)
+constexpr int kFinalThreads = 256;
+__global__ void __launch_bounds__(kFinalThreads)
+gram_final_kernel(double* __restrict__ G, const double* __restrict__ partial, int nparts, int RR) {
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (e < RR) {
+    int p = grp;
+    for (; p + 24 < nparts; p += 32) {
+      s0 += partial[(size_t)p * RR + e];
+      s1 += partial[(size_t)(p + 8) * RR + e];
+      s2 += partial[(size_t)(p + 16) * RR + e];
+      s3 += partial[(size_t)(p + 24) * RR + e];
+    }
+    for (; p < nparts; p += 8) s0 += partial[(size_t)p * RR + e];
+  }
+  red[grp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0 && e < RR)
+    G[e] = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
 }
-
-// G[e] = sum of the partials; SYM-produced partials are already mirrored
-__global__ void gram_final_kernel(double* __restrict__ G, const double* __restrict__ partial, int nparts, int RR) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= RR) return;
-  G[e] = sum_partials(partial, nparts, RR, e);
-}
+inline int final_grid(int RR) { return (RR + 31) / 32; }
 
 __global__ void axpy_lambda_kernel(double* __restrict__ Y, const double* __restrict__ X, double lambda, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,76 +383,88 @@ __global__ void cg_scale_cols_kernel(double* __restrict__ X, const double* __res
   for (; i < n; i += stride) X[i] *= norm[i % R];
 }
 
-// Solve A M = RHS for M (all R x R, row-major; A symmetric positive definite) by
-// Cholesky A = L L' in one CTA.  Generalises the closed-form 2x2 solve2sym
-// (linalg.h:77-88).  When partA / partRHS are given, A / RHS are first formed as the
-// slot-ordered sum of the partial Gram matrices (the second stage of the reductions above)
-// and written back.  status[0] is set to 1 when a pivot is not safely positive.
-// check != 0 also evaluates the stopping rule of bsbm_cg2 (cg.h:158): status[1] = 1 when every
-// diagonal entry of RHS is <= thr; otherwise status[2] (completed iterations) is incremented.
-// A stopped solver (status[0] or status[1] set) is left untouched.
-__global__ void small_solve_kernel(double* __restrict__ M, double* A, double* RHS, const double* __restrict__ partA, int nA,
-                                   const double* __restrict__ partRHS, int nRHS, int R, int* __restrict__ status, int check, double thr) {
-  __shared__ double L[32][33];
-  __shared__ double Bm[32][33];
-  __shared__ int bad;
+// Solve A M = RHS for M (all R x R, row-major; A symmetric positive definite) by Cholesky
+// A = L L' -- in ONE WARP: lane j keeps column j of A and of the right-hand side in registers, the
+// current column of L is broadcast through shared memory; no block barriers, every inner loop is a
+// run of independent FMAs.  Generalises the
+// closed-form 2x2 solve2sym (linalg.h:77-88); matrices are padded to 32 x 32 with the identity.
+// (A first version -- 1024 threads, three block barriers per pivot, substitution by dependent
+// chains through shared memory -- took 50-75 us; this one is a few microseconds, which matters
+// when an iteration is 2.5 ms on 8 GPUs.)
+// status[0] is set to 1 when a pivot is not safely positive.  check != 0 also evaluates the
+// stopping rule of bsbm_cg2 (cg.h:158): status[1] = 1 when every diagonal entry of RHS is
+// <= thr; otherwise status[2] (completed iterations) is incremented.  A stopped solver
+// (status[0] or status[1] set) is left untouched.
+__global__ void __launch_bounds__(32, 1)
+small_solve_kernel(double* __restrict__ M, const double* __restrict__ A, const double* __restrict__ RHS, int R,
+                   int* __restrict__ status, int check, double thr) {
+  __shared__ double S[32][33];      // L (lower triangle), written column by column during the factorisation
+  __shared__ double col[32];        // column k of L, broadcast to the warp
+  __shared__ double dinv[32];       // 1 / L[r][r]
   if (solver_stopped(status)) return;
-  const int tid = threadIdx.x;  // 32 x 32 threads: (i, j)
-  const int i = tid >> 5, j = tid & 31;
-  if (tid == 0) bad = 0;
-  if (i < R && j < R) {
-    const int e = i * R + j, RR = R * R;
-    double a, b;
-    if (nA > 0) {
-      a = sum_partials(partA, nA, RR, e);
-      A[e] = a;
-    } else {
-      a = A[e];
-    }
-    if (nRHS > 0) {
-      b = sum_partials(partRHS, nRHS, RR, e);
-      RHS[e] = b;
-    } else {
-      b = RHS[e];
-    }
-    L[i][j] = a;
-    Bm[i][j] = b;
+  const int j = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  double a[32], b[32];              // column j of A and of the right-hand side, padded with the identity / zeros
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const bool in = i < R && j < R;
+    a[i] = in ? A[i * R + j] : (i == j ? 1.0 : 0.0);
+    b[i] = in ? RHS[i * R + j] : 0.0;
   }
-  __syncthreads();
-  double amax = 0.0;
-  for (int d = 0; d < R; ++d) amax = fmax(amax, fabs(L[d][d]));
+  double ajj = 0.0, bjj = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { ajj = (i == j) ? a[i] : ajj; bjj = (i == j) ? b[i] : bjj; }
+  double amax = j < R ? fabs(ajj) : 0.0;                 // the identity padding does not take part in the pivot test
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) amax = fmax(amax, __shfl_xor_sync(full, amax, off));
   int done = 1;
-  if (check)
-    for (int d = 0; d < R; ++d)
-      if (!(Bm[d][d] <= thr)) done = 0;
-  __syncthreads();
-  for (int k = 0; k < R; ++k) {
-    if (tid == 0) {
-      const double piv = L[k][k];
-      if (!(piv > 1e-14 * amax)) { bad = 1; L[k][k] = 1.0; } else L[k][k] = sqrt(piv);
+  if (check) done = __all_sync(full, j >= R || bjj <= thr);
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    double piv = __shfl_sync(full, a[k], k);             // A[k][k] after the previous updates: lane k, register k
+    if (k < R && !(piv > 1e-14 * amax)) { bad = 1; piv = 1.0; }
+    const double inv = rsqrt(piv), root = piv * inv;     // one slow fp64 operation per pivot instead of sqrt + divide
+    if (j == k) {                                        // lane k publishes column k of L
+#pragma unroll
+      for (int i = 0; i < 32; ++i) col[i] = i > k ? a[i] * inv : (i == k ? root : 0.0);
+      dinv[k] = inv;
     }
-    __syncthreads();
-    if (j == k && i > k && i < R) L[i][k] /= L[k][k];
-    __syncthreads();
-    if (i > k && j > k && j <= i && i < R) L[i][j] -= L[i][k] * L[j][k];
-    __syncthreads();
+    __syncwarp();
+    const double ljk = col[j];
+    S[j][k] = ljk;
+    if (j > k) {                                         // trailing update of column j (rows below the pivot)
+#pragma unroll
+      for (int i = k + 1; i < 32; ++i) a[i] = fma(-col[i], ljk, a[i]);
+    }
+    __syncwarp();
   }
-  // forward / backward substitution, one right-hand-side column per thread of the first warp
-  if (i == 0 && j < R) {
-    for (int r = 0; r < R; ++r) {
-      double s = Bm[r][j];
-      for (int c = 0; c < r; ++c) s -= L[r][c] * Bm[c][j];
-      Bm[r][j] = s / L[r][r];
-    }
-    for (int r = R - 1; r >= 0; --r) {
-      double s = Bm[r][j];
-      for (int c = r + 1; c < R; ++c) s -= L[c][r] * Bm[c][j];
-      Bm[r][j] = s / L[r][r];
-    }
+  // lane j solves for column j of M with its right-hand side column in registers: forward (L z = b)
+  // and backward (L' m = z) substitution, right-looking so that the updates of a step are independent
+  // of each other.  The warp barrier after every step keeps ptxas from hoisting hundreds of
+  // shared-memory loads ahead (which spills).
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const double x = b[r] * dinv[r];
+    b[r] = x;
+#pragma unroll
+    for (int i = r + 1; i < 32; ++i) b[i] = fma(-S[i][r], x, b[i]);
+    __syncwarp();
   }
-  __syncthreads();
-  if (i < R && j < R) M[i * R + j] = Bm[i][j];
-  if (tid == 0) {
+#pragma unroll
+  for (int r = 31; r >= 0; --r) {
+    const double x = b[r] * dinv[r];
+    b[r] = x;
+#pragma unroll
+    for (int i = 0; i < r; ++i) b[i] = fma(-S[r][i], x, b[i]);
+    __syncwarp();
+  }
+  if (j < R) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < R) M[i * R + j] = b[i];
+  }
+  if (j == 0) {
     status[0] = bad;
     if (check) {
       status[1] = done;
@@ -542,7 +562,7 @@ int fsb_dense_gram_partial(double* dPartial, const double* dXa, const double* dX
 }
 
 int fsb_dense_gram_finalize(double* dG, const double* dPartial, int nparts, int R, cudaStream_t st) {
-  gram_final_kernel<<<(R * R + 255) / 256, 256, 0, st>>>(dG, dPartial, nparts, R * R);
+  gram_final_kernel<<<final_grid(R * R), kFinalThreads, 0, st>>>(dG, dPartial, nparts, R * R);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }
@@ -597,7 +617,10 @@ int fsb_dense_scale_cols(double* dX, const double* dNorm, long n, int R, cudaStr
 
 int fsb_dense_small_solve(double* dM, double* dA, double* dRHS, const double* dPartA, int nA, const double* dPartRHS, int nRHS, int R,
                           int* dStatus, int check, double thr, cudaStream_t st) {
-  small_solve_kernel<<<1, 1024, 0, st>>>(dM, dA, dRHS, dPartA, nA, dPartRHS, nRHS, R, dStatus, check, thr);
+  // second stage of the Gram reductions first (their own small parallel kernel), then the one-warp solve
+  if (nA > 0) FSB_TRY(fsb_dense_gram_finalize(dA, dPartA, nA, R, st));
+  if (nRHS > 0) FSB_TRY(fsb_dense_gram_finalize(dRHS, dPartRHS, nRHS, R, st));
+  small_solve_kernel<<<1, 32, 0, st>>>(dM, dA, dRHS, R, dStatus, check, thr);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }
@@ -640,7 +663,7 @@ extern "C" int fsb_rowmix_dev(int mode, double* dO, const double* dI, const doub
   int np = 0;
   if (rc == FSB_OK) rc = fsb_dense_mix_sub_gram(dO, dI, dM, dPart, n, R, nullptr, st, &np);
   if (rc == FSB_OK && G_host) {
-    gram_final_kernel<<<(R * R + 255) / 256, 256, 0, st>>>(dG, dPart, np, R * R);
+    gram_final_kernel<<<final_grid(R * R), kFinalThreads, 0, st>>>(dG, dPart, np, R * R);
     fsb_count_launch();
     e = cudaMemcpyAsync(G_host, dG, (size_t)R * R * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
