@@ -23,10 +23,11 @@ namespace {
 
 // FSB_CG_TRACE=1: wall-clock milliseconds of the solve's phases on stderr (allocation, set-up, every
 // status read-back) -- a debugging aid for gaps the kernel timings do not show
-bool cg_trace() {
-  static const bool on = [] { const char* e = getenv("FSB_CG_TRACE"); return e && *e && *e != '0'; }();
-  return on;
+int cg_trace_level() {
+  static const int lvl = [] { const char* e = getenv("FSB_CG_TRACE"); return e && *e ? atoi(e) : 0; }();
+  return lvl;
 }
+bool cg_trace() { return cg_trace_level() > 0; }
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -215,14 +216,18 @@ int shard_gram(CgShardWork& w, double* G, const double* Xa, const double* Xb, in
 
 // all-gather the local slices of every chunk of a sharded vector into the replicated layout
 int shard_allgather(CgShardWork& w, double* full, const double* loc, int R, cudaStream_t st) {
-  for (int c = 0; c < w.C; ++c)
-    FSB_TRY(fsb_comm_allgather(loc + (size_t)c * w.s * R, full + (size_t)c * w.Fc * R, (size_t)w.s * R, st));
-  return FSB_OK;
+  FSB_TRY(fsb_comm_group_start());   // the C per-chunk gathers go out as one fused NCCL launch
+  int rc = FSB_OK;
+  for (int c = 0; c < w.C && rc == FSB_OK; ++c)
+    rc = fsb_comm_allgather(loc + (size_t)c * w.s * R, full + (size_t)c * w.Fc * R, (size_t)w.s * R, st);
+  const int rc2 = fsb_comm_group_end();
+  return rc != FSB_OK ? rc : rc2;
 }
 
 // KP_loc = slice of sum_g A_g'(A_g P) + lambda P_loc
-int shard_apply_op(fsb_matrix* A, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st) {
+int shard_apply_op(fsb_matrix* A, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st, cudaEvent_t* trace = nullptr) {
   FSB_TRY(fsb_spmm_dev(A, w.tmp, w.Pfull, R, (void*)st));
+  if (trace) cudaEventRecord(trace[0], st);
   for (int c = 0; c < w.C; ++c) {
     const long r0 = c * w.Fc, r1 = std::min(w.F, r0 + w.Fc);
     if (r1 > r0) {
@@ -241,6 +246,7 @@ int shard_apply_op(fsb_matrix* A, fsb_matrix* T, CgShardWork& w, int R, double l
     FSB_CUDA(cudaStreamWaitEvent(w.comm_st, w.ev[c], 0));
     FSB_TRY(fsb_comm_reduce_scatter_sum(w.KPpart + (size_t)c * w.Fc * R, w.KPl + (size_t)c * w.s * R, (size_t)w.s * R, w.comm_st));
   }
+  if (trace) cudaEventRecord(trace[1], st);
   FSB_CUDA(cudaEventRecord(w.ev_done, w.comm_st));
   FSB_CUDA(cudaStreamWaitEvent(st, w.ev_done, 0));
   if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(w.KPl, w.Pl, lambda, w.nloc * R, st));
@@ -286,20 +292,30 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   int queued = 0, np = 0;
   w.h_status[0] = w.h_status[1] = w.h_status[2] = 0;
   double t_prev = 0.0;
+  cudaEvent_t pe[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6], [7]: inside the operator
+  if (cg_trace_level() >= 2)
+    for (auto& e : pe) cudaEventCreate(&e);
   if (cg_trace()) { cudaStreamSynchronize(st); t_prev = now_ms(); }
   while (queued < max_iter) {
     const int nb = std::min(batch, max_iter - queued);
     for (int k = 0; k < nb; ++k) {
-      FSB_TRY(shard_apply_op(A, T, w, R, lambda, st));
+      const bool ph = cg_trace_level() >= 2 && k == 0;      // FSB_CG_TRACE=2: device time of the phases of an iteration
+      if (ph) cudaEventRecord(pe[0], st);
+      FSB_TRY(shard_apply_op(A, T, w, R, lambda, st, ph ? pe + 6 : nullptr));
+      if (ph) cudaEventRecord(pe[1], st);
       FSB_TRY(shard_gram(w, w.PtKP, w.Pl, w.KPl, R, st));
       FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, w.G1, nullptr, 0, nullptr, 0, R, w.status, 0, 0.0, st));
+      if (ph) cudaEventRecord(pe[2], st);
       FSB_TRY(fsb_dense_mix_add(w.Xl, w.Pl, w.Alpha, w.nloc, R, w.status, st));
       FSB_TRY(fsb_dense_mix_sub_gram(w.Rl, w.KPl, w.Alpha, w.partial, w.nloc, R, w.status, st, &np));
       FSB_TRY(fsb_dense_gram_finalize(w.G2, w.partial, np, R, st));
       FSB_TRY(fsb_allreduce_sum_dev(w.G2, (long)R * R, (void*)st));
       FSB_TRY(fsb_dense_small_solve(w.Psi, w.G1, w.G2, nullptr, 0, nullptr, 0, R, w.status, 1, thr, st));
+      if (ph) cudaEventRecord(pe[3], st);
       FSB_TRY(fsb_dense_mix_set(w.Pl, w.Pl, w.Rl, w.Psi, w.nloc, R, w.status, st));
+      if (ph) cudaEventRecord(pe[4], st);
       FSB_TRY(shard_allgather(w, w.Pfull, w.Pl, R, st));
+      if (ph) cudaEventRecord(pe[5], st);
       std::swap(w.G1, w.G2);
     }
     queued += nb;
@@ -309,11 +325,22 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
       const double t = now_ms();
       fprintf(stderr, "[fsb cg %d/%d] iterations %d..%d: %.3f ms (status %d %d %d)\n", w.rank, w.G, queued - nb, queued - 1, t - t_prev,
               w.h_status[0], w.h_status[1], w.h_status[2]);
-      t_prev = t;
+      if (cg_trace_level() >= 2) {
+        float ms[5];
+        for (int q = 0; q < 5; ++q) cudaEventElapsedTime(&ms[q], pe[q], pe[q + 1]);
+        float op[3];
+        cudaEventElapsedTime(&op[0], pe[0], pe[6]); cudaEventElapsedTime(&op[1], pe[6], pe[7]); cudaEventElapsedTime(&op[2], pe[7], pe[1]);
+        if (w.rank == 0)
+          fprintf(stderr, "[fsb cg %d/%d]   device ms: operator %.3f (A P %.3f, A' chunks %.3f, reduce-scatter tail + lambda P %.3f) | "
+                          "P'KP + allreduce + solve %.3f | X, R updates + R'R + allreduce + solve %.3f | P update %.3f | all-gather of P %.3f\n",
+                  w.rank, w.G, ms[0], op[0], op[1], op[2], ms[1], ms[2], ms[3], ms[4]);
+      }
+      t_prev = now_ms();
     }
     if (w.h_status[0] || w.h_status[1]) break;
   }
   const int it = w.h_status[2];
+  for (auto& e : pe) if (e) cudaEventDestroy(e);
   // X = X_loc diag(norm), gathered into the replicated result (through the partial buffer: padded rows)
   for (int c = 0; c < w.C; ++c) FSB_TRY(fsb_dense_scale_cols(w.Xl + (size_t)c * w.s * R, w.norm, w.s, R, st));
   FSB_TRY(shard_allgather(w, w.KPpart, w.Xl, R, st));

@@ -22,6 +22,7 @@ typedef int (*fn_init_rank)(nccl_comm*, int, nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
 typedef int (*fn_reduce_scatter)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t);
 typedef int (*fn_allgather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t);
+typedef int (*fn_group)(void);
 typedef int (*fn_destroy)(nccl_comm);
 typedef const char* (*fn_errstr)(int);
 
@@ -32,6 +33,7 @@ struct Nccl {
   fn_allreduce allreduce = nullptr;
   fn_reduce_scatter reduce_scatter = nullptr;
   fn_allgather allgather = nullptr;
+  fn_group group_start = nullptr, group_end = nullptr;
   fn_destroy destroy = nullptr;
   fn_errstr errstr = nullptr;
 } g_nccl;
@@ -53,6 +55,8 @@ int load_nccl() {
   g_nccl.allreduce = (fn_allreduce)dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.reduce_scatter = (fn_reduce_scatter)dlsym(g_nccl.lib, "ncclReduceScatter");
   g_nccl.allgather = (fn_allgather)dlsym(g_nccl.lib, "ncclAllGather");
+  g_nccl.group_start = (fn_group)dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.group_end = (fn_group)dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.destroy = (fn_destroy)dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.errstr = (fn_errstr)dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.reduce_scatter || !g_nccl.allgather || !g_nccl.destroy) {
@@ -75,6 +79,18 @@ int fsb_comm_reduce_scatter_sum(const double* send, double* recv, size_t recvcou
   if (!fsb_comm_active()) return fsb_set_error(FSB_ENCCL, "reduce-scatter without an active communicator");
   const int rc = g_nccl.reduce_scatter(send, recv, recvcount, /*ncclFloat64*/ 8, /*ncclSum*/ 0, g_comm, st);
   return rc ? nccl_fail(rc, "ncclReduceScatter") : FSB_OK;
+}
+
+// several collectives issued between these two calls are fused by NCCL into one launch
+int fsb_comm_group_start() {
+  if (!fsb_comm_active() || !g_nccl.group_start) return FSB_OK;
+  const int rc = g_nccl.group_start();
+  return rc ? nccl_fail(rc, "ncclGroupStart") : FSB_OK;
+}
+int fsb_comm_group_end() {
+  if (!fsb_comm_active() || !g_nccl.group_end) return FSB_OK;
+  const int rc = g_nccl.group_end();
+  return rc ? nccl_fail(rc, "ncclGroupEnd") : FSB_OK;
 }
 
 // recv[nranks*sendcount] = concatenation of every rank's send[sendcount] in rank order

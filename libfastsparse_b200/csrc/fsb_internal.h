@@ -124,3 +124,5 @@ int fsb_dense_axpy_lambda(double* dY, const double* dX, double lambda, long n, c
 bool fsb_comm_active();
 int fsb_comm_reduce_scatter_sum(const double* send, double* recv, size_t recvcount, cudaStream_t st);
 int fsb_comm_allgather(const double* send, double* recv, size_t sendcount, cudaStream_t st);
+int fsb_comm_group_start();
+int fsb_comm_group_end();
