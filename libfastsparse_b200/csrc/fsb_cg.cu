@@ -148,7 +148,7 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
 // The F rows are cut into C chunks of Fc rows, every chunk into G slices of s rows; rank g owns slice g
 // of every chunk (local layout [C][s][R]).  The dense passes are row-local, so the layout is invisible
 // to them.  Rows are padded with zeros to C*G*s.
-constexpr int kMaxChunks = 4;
+constexpr int kMaxChunks = 8;
 
 struct CgShardWork {
   int G = 1, rank = 0, C = 1;
@@ -158,7 +158,7 @@ struct CgShardWork {
   double *partial = nullptr;
   int *status = nullptr, *h_status = nullptr;
   cudaStream_t comm_st = nullptr;
-  cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_done = nullptr;
   void release() {
     cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
@@ -175,7 +175,10 @@ struct CgShardWork {
 void shard_layout(long F, int R, int G, int* C, long* s, long* Fc, long* Fp, long* nloc) {
   // chunks only pay off when a chunk is a sizeable transfer; R = 1 keeps one chunk (its products may
   // take the merge-path kernel, which caches per-handle state and must see the whole matrix)
-  *C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? kMaxChunks : 1;
+  // (four chunks: eight shorten the exposed tail -- the last chunk's reduce-scatter -- from 0.17 to 0.14 ms
+  // on 8 GPUs at C5 but the smaller product launches lose 0.2 ms, profiles/r1i_cg_trace_n8_8chunks.log)
+  (void)G;
+  *C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? 4 : 1;
   *s = (F + (long)*C * G - 1) / ((long)*C * G);
   if ((*s * R) % 2) *s += 1;            // keep every slice 16-byte aligned for the vector paths
   *Fc = *s * G; *Fp = *Fc * *C; *nloc = *s * *C;
