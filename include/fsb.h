@@ -146,6 +146,14 @@ int fsb_cg_host(fsb_matrix_t A, fsb_matrix_t At, double* X, const double* B, int
 int fsb_cg_dev(fsb_matrix_t A, fsb_matrix_t At, double* dX, const double* dB, int R,
                double lambda, double tol, int max_iter, int* out_iter, void* stream);
 
+/* ------------------------------- device memory without the CUDA toolkit */
+/* For plain C callers of the *_dev face (examples/sampler_loop.c): buffers on the library's
+ * device, copies ordered after the library's default stream (stream = NULL in the *_dev calls). */
+void* fsb_device_malloc(size_t bytes);                 /* NULL on failure (fsb_last_error) */
+int fsb_device_free(void* p);
+int fsb_copy_to_device(void* dst_dev, const void* src_host, size_t bytes);
+int fsb_copy_to_host(void* dst_host, const void* src_dev, size_t bytes);
+
 /* ------------------------------- Macau-style caller loop */
 /* d[i] = standard normal, a pure function of (seed, i) (counter-based Box-Muller); the host twin
  * regenerates the same stream (to the last ulps of libm) for checks. */

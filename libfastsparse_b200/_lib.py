@@ -56,6 +56,10 @@ _SIGS = {
     "fsb_ata_pair_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "fsb_cg_host": (C.c_int, [handle, handle, c_dbl_p, c_dbl_p, C.c_int, C.c_double, C.c_double, C.c_int, c_int_p]),
     "fsb_cg_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, c_int_p, C.c_void_p]),
+    "fsb_device_malloc": (C.c_void_p, [C.c_size_t]),
+    "fsb_device_free": (C.c_int, [C.c_void_p]),
+    "fsb_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fsb_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fsb_randn_dev": (C.c_int, [C.c_void_p, C.c_long, C.c_ulonglong, C.c_void_p]),
     "fsb_randn_host": (C.c_int, [c_dbl_p, C.c_long, C.c_ulonglong]),
     "fsb_noise_rhs_dev": (C.c_int, [handle, handle, C.c_void_p, C.c_int, C.c_double, C.c_ulonglong, C.c_void_p]),

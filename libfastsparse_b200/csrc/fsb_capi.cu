@@ -410,6 +410,37 @@ int fsb_ata_pair_dev(fsb_matrix_t A, fsb_matrix_t At, double* dY, const double* 
   return FSB_OK;
 }
 
+// ---- device memory for callers without the CUDA toolkit (a plain C program linking only this library)
+void* fsb_device_malloc(size_t bytes) {
+  if (fsb_require_device() != FSB_OK) return nullptr;
+  void* p = nullptr;
+  const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) { fsb_cuda_error(e, "fsb_device_malloc", __FILE__, __LINE__); return nullptr; }
+  return p;
+}
+
+int fsb_device_free(void* p) {
+  if (!p) return FSB_OK;
+  FSB_CUDA(cudaFree(p));
+  return FSB_OK;
+}
+
+int fsb_copy_to_device(void* dst_dev, const void* src_host, size_t bytes) {
+  FSB_TRY(fsb_require_device());
+  if (bytes && (!dst_dev || !src_host)) return fsb_set_error(FSB_EINVAL, "fsb_copy_to_device: null argument");
+  FSB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, g_stream));
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  return FSB_OK;
+}
+
+int fsb_copy_to_host(void* dst_host, const void* src_dev, size_t bytes) {
+  FSB_TRY(fsb_require_device());
+  if (bytes && (!dst_host || !src_dev)) return fsb_set_error(FSB_EINVAL, "fsb_copy_to_host: null argument");
+  FSB_CUDA(cudaStreamSynchronize(g_stream));
+  FSB_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return FSB_OK;
+}
+
 // The right-hand side of a Macau-style sampling step (bench_a_mul_b.c:334-347): B = A'N + sqrt(lambda) E
 // with fresh standard-normal N [nrow][R] and E [ncol][R].  Everything happens in HBM next to the
 // resident matrix: the noise is generated by a counter-based kernel, and sqrt(lambda) E is added in

@@ -45,6 +45,14 @@ def test_dropin_c_acceptance():
 
 
 @pytest.mark.gpu
+def test_c_example_sampler_loop(tmp_path):
+    """examples/sampler_loop.c: plain C on the C ABI alone -- file straight into HBM, device noise, block-CG solves."""
+    _ensure_built()
+    r = _run("sampler_loop", "data/sbm-100-50.data", "8", "3")
+    assert r.returncode == 0 and "SAMPLER LOOP OK" in r.stdout and r.stdout.count("iterations") == 3, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_reference_test_sparse_unmodified_passes_on_gpu():
     r = _run("ref_test_sparse")
     assert r.returncode == 0, r.stdout + r.stderr
