@@ -293,7 +293,9 @@ int fsb_tune_csr_staged(int deep);
 int fsb_tune_formats(int native);
 /* multi-GPU block CG: 0 (default) = CG vectors sharded over the unknowns (reduce-scatter of the
  * A'(A P) partial overlapped with its computation, all-gather of P, allreduce of the R x R Grams);
- * 1 = replicated vectors with one allreduce of the [F][R] partial per iteration. */
+ * 1 = replicated vectors with one allreduce of the [F][R] partial per iteration;
+ * 3 = like 0 with P all-gathered as two column halves, the second travelling behind the first column
+ *     pass of the next product (measured: no gain on 8 GPUs; kept for experiments). */
 int fsb_tune_cg_dist(int mode);
 
 /* ------------------------------------------ synthetic inputs (bench) */

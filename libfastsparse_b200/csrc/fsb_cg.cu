@@ -149,18 +149,24 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
 // of every chunk (local layout [C][s][R]).  The dense passes are row-local, so the layout is invisible
 // to them.  Rows are padded with zeros to C*G*s.
 constexpr int kMaxChunks = 8;
+// 0 (and 2) = sharded vectors, 1 = replicated vectors + one allreduce,
+// 3 = sharded vectors with P all-gathered as two column halves behind the next product's first pass
+int g_cg_dist_mode = 0;
 
 struct CgShardWork {
   int G = 1, rank = 0, C = 1;
   long F = 0, Fc = 0, s = 0, Fp = 0, nloc = 0;
   double *Pfull = nullptr, *KPpart = nullptr, *Xl = nullptr, *Rl = nullptr, *Pl = nullptr, *KPl = nullptr, *tmp = nullptr;
+  double* Psend = nullptr;          // column halves of P_loc, the send buffers of the split all-gather
   double *G1 = nullptr, *G2 = nullptr, *PtKP = nullptr, *Alpha = nullptr, *Psi = nullptr, *norm = nullptr, *inorm = nullptr;
   double *partial = nullptr;
   int *status = nullptr, *h_status = nullptr;
   cudaStream_t comm_st = nullptr;
   cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_done = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_lo = nullptr, ev_hi = nullptr;
   void release() {
+    cudaFree(Psend);
+    for (cudaEvent_t e : {ev_p, ev_lo, ev_hi}) if (e) cudaEventDestroy(e);
     cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
     cudaFree(G1); cudaFree(G2); cudaFree(PtKP); cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial);
     cudaFree(status);
@@ -190,6 +196,7 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8, rr = (size_t)R * R * 8;
   FSB_CUDA(cudaMalloc(&w.Pfull, full)); FSB_CUDA(cudaMalloc(&w.KPpart, full));
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
+  FSB_CUDA(cudaMalloc(&w.Psend, loc));
   FSB_CUDA(cudaMalloc(&w.tmp, std::max<size_t>((size_t)Nloc * R, 1) * 8));
   FSB_CUDA(cudaMalloc(&w.G1, rr)); FSB_CUDA(cudaMalloc(&w.G2, rr)); FSB_CUDA(cudaMalloc(&w.PtKP, rr));
   FSB_CUDA(cudaMalloc(&w.Alpha, rr)); FSB_CUDA(cudaMalloc(&w.Psi, rr));
@@ -200,6 +207,9 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   FSB_CUDA(cudaStreamCreateWithFlags(&w.comm_st, cudaStreamNonBlocking));
   for (auto& e : w.ev) FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   FSB_CUDA(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&w.ev_p, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&w.ev_lo, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&w.ev_hi, cudaEventDisableTiming));
   return FSB_OK;
 }
 
@@ -228,8 +238,35 @@ int shard_allgather(CgShardWork& w, double* full, const double* loc, int R, cuda
 }
 
 // KP_loc = slice of sum_g A_g'(A_g P) + lambda P_loc
-int shard_apply_op(fsb_matrix* A, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st, cudaEvent_t* trace = nullptr) {
-  FSB_TRY(fsb_spmm_dev(A, w.tmp, w.Pfull, R, (void*)st));
+// all-gather of the new P as two column halves on the second stream, so that the first column pass of
+// the next A_g P starts as soon as the first half has arrived (the second half travels behind it)
+int shard_allgather_halves(CgShardWork& w, int R, cudaStream_t st) {
+  const int h = R / 2;
+  double *lo = w.Psend, *hi = w.Psend + (size_t)w.nloc * h;
+  FSB_TRY(fsb_dense_split_halves(lo, hi, w.Pl, w.nloc, R, w.status, st));
+  FSB_CUDA(cudaEventRecord(w.ev_p, st));
+  FSB_CUDA(cudaStreamWaitEvent(w.comm_st, w.ev_p, 0));
+  for (int half = 0; half < 2; ++half) {
+    const double* send = half ? hi : lo;
+    double* recv = w.Pfull + (half ? (size_t)w.Fp * h : 0);
+    FSB_TRY(fsb_comm_group_start());
+    int rc = FSB_OK;
+    for (int c = 0; c < w.C && rc == FSB_OK; ++c)
+      rc = fsb_comm_allgather(send + (size_t)c * w.s * h, recv + (size_t)c * w.Fc * h, (size_t)w.s * h, w.comm_st);
+    const int rc2 = fsb_comm_group_end();
+    if (rc != FSB_OK || rc2 != FSB_OK) return rc != FSB_OK ? rc : rc2;
+    FSB_CUDA(cudaEventRecord(half ? w.ev_hi : w.ev_lo, w.comm_st));
+  }
+  return FSB_OK;
+}
+
+int shard_apply_op(fsb_matrix* A, fsb_matrix* Acsr, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st, bool halves,
+                   cudaEvent_t* trace = nullptr) {
+  if (halves) {   // P arrived as column halves (shard_allgather_halves): one column pass per half
+    FSB_TRY(fsb_launch_csr_spmm_halves(Acsr, w.tmp, w.Pfull, w.Pfull + (size_t)w.Fp * (R / 2), R, st, w.ev_lo, w.ev_hi));
+  } else {
+    FSB_TRY(fsb_spmm_dev(A, w.tmp, w.Pfull, R, (void*)st));
+  }
   if (trace) cudaEventRecord(trace[0], st);
   for (int c = 0; c < w.C; ++c) {
     const long r0 = c * w.Fc, r1 = std::min(w.F, r0 + w.Fc);
@@ -260,13 +297,15 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
                    int max_iter, int* out_iter, cudaStream_t st, CgShardWork& w) {
   const long F = A->ncol;
   if (max_iter <= 0) max_iter = (int)F;
-  fsb_matrix* T = nullptr;
+  fsb_matrix *T = nullptr, *Acsr = nullptr;
+  FSB_TRY(csr_face(A, st, &Acsr));
   if (At) {
     FSB_TRY(csr_face(At, st, &T));
   } else {
     FSB_TRY(fsb_build_transpose(A, st));
     T = A->T;
   }
+  bool halves = false;   // P currently stored as two column halves in Pfull
   const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8;
   FSB_CUDA(cudaMemsetAsync(w.status, 0, kStatusWords * sizeof(int), st));
   FSB_CUDA(cudaMemsetAsync(w.KPpart, 0, full, st));     // the padding rows stay zero for the whole solve
@@ -304,7 +343,7 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
     for (int k = 0; k < nb; ++k) {
       const bool ph = cg_trace_level() >= 2 && k == 0;      // FSB_CG_TRACE=2: device time of the phases of an iteration
       if (ph) cudaEventRecord(pe[0], st);
-      FSB_TRY(shard_apply_op(A, T, w, R, lambda, st, ph ? pe + 6 : nullptr));
+      FSB_TRY(shard_apply_op(A, Acsr, T, w, R, lambda, st, halves, ph ? pe + 6 : nullptr));
       if (ph) cudaEventRecord(pe[1], st);
       FSB_TRY(shard_gram(w, w.PtKP, w.Pl, w.KPl, R, st));
       FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, w.G1, nullptr, 0, nullptr, 0, R, w.status, 0, 0.0, st));
@@ -317,7 +356,17 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
       if (ph) cudaEventRecord(pe[3], st);
       FSB_TRY(fsb_dense_mix_set(w.Pl, w.Pl, w.Rl, w.Psi, w.nloc, R, w.status, st));
       if (ph) cudaEventRecord(pe[4], st);
-      FSB_TRY(shard_allgather(w, w.Pfull, w.Pl, R, st));
+      // optional (fsb_tune_cg_dist(3)): the next product takes P as two column halves, so that the second half's
+      // all-gather can travel behind the first column pass.  Measured on 8 GPUs at C5 it gains nothing -- the
+      // product slows down by what the hidden transfer saves (1.08 ms either way, profiles/r1i_cg_trace_n8_halves.log)
+      // -- so the plain all-gather stays the default.
+      const bool want_halves = g_cg_dist_mode == 3 && R % 4 == 0 && (R / 2) * 8 >= 128;
+      if (want_halves) {
+        FSB_TRY(shard_allgather_halves(w, R, st));
+      } else {
+        FSB_TRY(shard_allgather(w, w.Pfull, w.Pl, R, st));
+      }
+      halves = want_halves;
       if (ph) cudaEventRecord(pe[5], st);
       std::swap(w.G1, w.G2);
     }
@@ -355,7 +404,6 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   return FSB_OK;
 }
 
-int g_cg_dist_mode = 0;   // 0 = sharded vectors when a communicator is active, 1 = replicated vectors + allreduce
 
 // The workspace of a solve (a few [F][R] vectors and the [N][R] intermediate: 3.6 GB at C5) stays
 // with the handle between solves -- a sampler calls the solver thousands of times on one matrix, and
@@ -377,7 +425,7 @@ void cg_cache_free(void* p) {
 // one solve through whichever path applies to the handle
 int cg_solve(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, double lambda, double tol, int max_iter,
              int* out_iter, cudaStream_t st) {
-  const bool shard = A->sharded && fsb_comm_active() && g_cg_dist_mode == 0 && (long)A->ncol >= 64L * fsb_comm_size();
+  const bool shard = A->sharded && fsb_comm_active() && g_cg_dist_mode != 1 && (long)A->ncol >= 64L * fsb_comm_size();
   const int kind = shard ? 2 : 1, G = shard ? fsb_comm_size() : 1;
   const double t0 = cg_trace() ? now_ms() : 0.0;
   CgCache* c = static_cast<CgCache*>(A->cg_cache);
@@ -412,7 +460,7 @@ extern "C" int fsb_cg_shard_layout(long F, int R, int G, int* C, long* s, long* 
 }
 
 extern "C" int fsb_tune_cg_dist(int mode) {
-  if (mode < 0 || mode > 1) return fsb_set_error(FSB_EINVAL, "fsb_tune_cg_dist: mode must be 0 (sharded vectors) or 1 (replicated)");
+  if (mode < 0 || mode > 3) return fsb_set_error(FSB_EINVAL, "fsb_tune_cg_dist: mode must be 0 (sharded vectors), 1 (replicated), 2 (sharded, plain all-gather) or 3 (sharded, split all-gather forced)");
   g_cg_dist_mode = mode;
   return FSB_OK;
 }

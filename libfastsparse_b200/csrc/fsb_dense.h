@@ -19,6 +19,8 @@ int fsb_dense_mix_sub_gram(double* dO, const double* dI, const double* dM, doubl
                            cudaStream_t st, int* nparts);                                                                   // O -= I M; partial = O'O
 int fsb_dense_mix_set(double* dO, const double* dI, const double* dAdd, const double* dM, long n, int R, const int* dStatus,
                       cudaStream_t st);                                                                                     // O = Add + I M (I may alias O)
+// column halves of a [n][R] operand into two [n][R/2] arrays (a stopped solver skips the pass)
+int fsb_dense_split_halves(double* dLo, double* dHi, const double* dSrc, long n, int R, const int* dStatus, cudaStream_t st);
 int fsb_dense_scale_cols(double* dX, const double* dNorm, long n, int R, cudaStream_t st);
 // M = A^-1 RHS; A / RHS are first summed from partial Grams when nA / nRHS > 0 (and written back)
 int fsb_dense_small_solve(double* dM, double* dA, double* dRHS, const double* dPartA, int nA, const double* dPartRHS, int nRHS, int R,

@@ -96,8 +96,14 @@ int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, 
 // tuning override for the sweep tool: TW, G, VEC, slabs (0 = heuristic)
 void fsb_csr_spmm_set_tuning(int tw, int g, int vec, int slabs);
 // ---- kernels_csr_staged.cu
+// ldx > 0: the dense operand of this pass is a column slab stored on its own ([ncol][ldx], first column xcol0)
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0, bool deep = false);
+                               int g, int vec, cudaStream_t st, const double* dZ = nullptr, double lambda = 0.0, bool deep = false,
+                               int ldx = 0, int xcol0 = 0);
+// Y = A X with X given as two column halves Xlo, Xhi ([ncol][R/2] each): two column passes, each waiting on
+// the event that says its half has arrived (the all-gather of the sharded CG, fsb_cg.cu).  R even, R/2 * 8 >= 128.
+int fsb_launch_csr_spmm_halves(fsb_matrix* A, double* dY, const double* dXlo, const double* dXhi, int R, cudaStream_t st,
+                               cudaEvent_t ready_lo, cudaEvent_t ready_hi);
 // a row-range alias of a CSR handle (row_ptr offset, shared cols / vals) inherits and returns the autotune state
 inline void fsb_copy_tuning(fsb_matrix* dst, const fsb_matrix* src) {
   dst->tuned_R = src->tuned_R; dst->tuned_passes = src->tuned_passes; dst->tuned_deep = src->tuned_deep;

@@ -404,6 +404,21 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st, dZ, lambda, A->tuned_deep != 0);
 }
 
+int fsb_launch_csr_spmm_halves(fsb_matrix* A, double* dY, const double* dXlo, const double* dXhi, int R, cudaStream_t st,
+                               cudaEvent_t ready_lo, cudaEvent_t ready_hi) {
+  const int half = R / 2;
+  if (R % 2 || half * 8 < 128 || half > 64 || (((uintptr_t)dXlo | (uintptr_t)dXhi | (uintptr_t)dY) & 15))
+    return fsb_set_error(FSB_EINVAL, "spmm (column halves): unsupported width or alignment (R=%d)", R);
+  if (A->nrow == 0) return FSB_OK;
+  const int vec = 2, g = pow2_ceil(half / vec);
+  const bool deep = A->tuned_R == R ? A->tuned_deep != 0 : true;
+  if (ready_lo) FSB_CUDA(cudaStreamWaitEvent(st, ready_lo, 0));
+  FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dXlo, R, 0, half, g, vec, st, nullptr, 0.0, deep, half, 0));
+  if (ready_hi) FSB_CUDA(cudaStreamWaitEvent(st, ready_hi, 0));
+  FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dXhi, R, half, half, g, vec, st, nullptr, 0.0, deep, half, 0));
+  return FSB_OK;
+}
+
 int fsb_launch_csr_ata_fused(const fsb_matrix* A, double* dY, const double* dX, int R, double lambda, cudaStream_t st) {
   if (R <= 0 || R > 32) return fsb_set_error(FSB_EINVAL, "fused A'A: R must be 1..32 (got %d)", R);
   const long long n = (long long)A->ncol * R;

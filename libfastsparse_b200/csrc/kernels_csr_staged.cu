@@ -57,7 +57,7 @@ template <> __device__ __forceinline__ void pin_after_loads<4>(double (&x)[4]) {
 // One row, summed strictly in stored order, gathers issued in batches of U.
 template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
-                                         double (&acc)[VEC], const double* __restrict__ xbase, int R, bool col_ok,
+                                         double (&acc)[VEC], const double* __restrict__ xbase, int ldx, bool col_ok,
                                          unsigned long long xpol) {
   constexpr int U = FSB_STAGED_U;
   for (int i = s; i < e; i += U) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
       if (idx < e && col_ok) {
         const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
         if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
-        XLoad<VEC>::ldp(xr[u], xbase + (long long)c * R, xpol);
+        XLoad<VEC>::ldp(xr[u], xbase + (long long)c * ldx, xpol);
       } else {
         if (VALS) vv[u] = 0.0;
 #pragma unroll
@@ -99,7 +99,7 @@ template <int G, int VEC, bool VALS, bool DEEP>
 __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                                             int R, int col0, int ncols, int RB, int CAP, int l2mode,
-                                            const double* __restrict__ Z, double lambda) {
+                                            const double* __restrict__ Z, double lambda, int ldx, int xcol0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -115,7 +115,8 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   const int r0 = blockIdx.x * RB;
   const int nr = min(RB, nrow - r0);
   const bool col_ok = l * VEC < ncols;
-  const double* xbase = X + col0 + l * VEC;
+  // the dense operand may be a column slab stored on its own: row stride ldx, first column xcol0
+  const double* xbase = X + xcol0 + l * VEC;
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
   const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
@@ -135,7 +136,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true, DEEP>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, R, col_ok, xpol);
+      walk_row<G, VEC, VALS, true, DEEP>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -156,7 +157,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, cs, ce, acc, xbase, R, col_ok, xpol);
+      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, cs, ce, acc, xbase, ldx, col_ok, xpol);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -176,7 +177,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, s, e, acc, xbase, R, col_ok, xpol);
+      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, s, e, acc, xbase, ldx, col_ok, xpol);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -190,46 +191,48 @@ template <int G, int VEC, bool VALS>
 __global__ void __launch_bounds__(kThreads)
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                       int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
-  staged_body<G, VEC, VALS, false>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda);
+                       int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
+                       int ldx, int xcol0) {
+  staged_body<G, VEC, VALS, false>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0);
 }
 
 template <int G, int VEC, bool VALS>
 __global__ void __launch_bounds__(kThreads, FSB_STAGED_DEEP_MINB)
 csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                            int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda) {
-  staged_body<G, VEC, VALS, true>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda);
+                            int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
+                            int ldx, int xcol0) {
+  staged_body<G, VEC, VALS, true>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0);
 }
 
 int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 
 template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-           const double* dZ, double lambda, bool deep) {
+           const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
   auto kern = deep ? csr_spmm_staged_deep_kernel<G, VEC, VALS> : csr_spmm_staged_kernel<G, VEC, VALS>;
   size_t body = std::max((size_t)CAP * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
-  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda);
+  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, ldx, xcol0);
   return FSB_OK;
 }
 
 template <int G, int VEC>
 int launch_v(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-             const double* dZ, double lambda, bool deep) {
-  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep)
-                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
+             const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
+  return A->has_vals ? launch<G, VEC, true>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep, ldx, xcol0)
+                     : launch<G, VEC, false>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep, ldx, xcol0);
 }
 
 template <int G>
 int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
-             const double* dZ, double lambda, bool deep) {
+             const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
   switch (vec) {
-    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
-    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
-    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep);
+    case 1: return launch_v<G, 1>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep, ldx, xcol0);
+    case 2: return launch_v<G, 2>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep, ldx, xcol0);
+    default: return launch_v<G, 4>(A, dY, dX, R, col0, ncols, RB, CAP, st, dZ, lambda, deep, ldx, xcol0);
   }
 }
 
@@ -243,7 +246,8 @@ void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
 
 // one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
 int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols,
-                               int g, int vec, cudaStream_t st, const double* dZ, double lambda, bool deep) {
+                               int g, int vec, cudaStream_t st, const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
+  if (ldx <= 0) { ldx = R; xcol0 = col0; }   // the usual case: X is [ncol][R] like Y
   // rows per CTA: enough rows that every sub-group gets a few, bounded so that the index
   // run (~avg_nnz * RB entries) stays a small shared-memory footprint (several CTAs per SM)
   const int nt = kThreads / g;
@@ -256,12 +260,12 @@ int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX
   cap = std::max((cap + 63) & ~63, 512);
   int rc;
   switch (g) {
-    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
-    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
-    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
-    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
-    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
-    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep); break;
+    case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
+    case 2: rc = launch_g<2>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
+    case 4: rc = launch_g<4>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
+    case 8: rc = launch_g<8>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
+    case 16: rc = launch_g<16>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
+    default: rc = launch_g<32>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
   }
   FSB_TRY(rc);
   FSB_KERNEL_CHECK();

@@ -377,6 +377,21 @@ cg_mix_kernel(double* O, const double* I, const double* Add, const double* __res
   }
 }
 
+// lo[i][0:h] = src[i][0:h], hi[i][0:h] = src[i][h:2h]  (column halves of a [n][2h] operand, 16-byte pieces)
+__global__ void split_halves_kernel(double2* __restrict__ lo, double2* __restrict__ hi, const double2* __restrict__ src,
+                                    long long n, int h2 /* half width in double2 */, const int* __restrict__ status) {
+  if (solver_stopped(status)) return;
+  const long long tot = n * 2 * h2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < tot; i += stride) {
+    const long long row = i / (2 * h2);
+    const int c = (int)(i - row * 2 * h2);
+    const double2 v = src[i];
+    if (c < h2) lo[row * h2 + c] = v; else hi[row * h2 + (c - h2)] = v;
+  }
+}
+
 __global__ void cg_scale_cols_kernel(double* __restrict__ X, const double* __restrict__ norm, long long n, int R) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -605,6 +620,15 @@ int fsb_dense_mix_sub_gram(double* dO, const double* dI, const double* dM, doubl
 
 int fsb_dense_mix_set(double* dO, const double* dI, const double* dAdd, const double* dM, long n, int R, const int* dStatus, cudaStream_t st) {
   return dispatch_mix<2>(dO, dI, dAdd, dM, nullptr, n, R, dStatus, st, nullptr);
+}
+
+int fsb_dense_split_halves(double* dLo, double* dHi, const double* dSrc, long n, int R, const int* dStatus, cudaStream_t st) {
+  if (R % 4 || !aligned16(dLo) || !aligned16(dHi) || !aligned16(dSrc)) return fsb_set_error(FSB_EINVAL, "split halves: R must be a multiple of 4, operands 16-byte aligned");
+  if (n <= 0) return FSB_OK;
+  split_halves_kernel<<<grid_for((long long)n * R / 2), 256, 0, st>>>(reinterpret_cast<double2*>(dLo), reinterpret_cast<double2*>(dHi),
+                                                                   reinterpret_cast<const double2*>(dSrc), n, R / 4, dStatus);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
 }
 
 int fsb_dense_scale_cols(double* dX, const double* dNorm, long n, int R, cudaStream_t st) {

@@ -57,7 +57,8 @@ def main():
         # block CG on the shard vs on the full matrix
         Xf, itf = full.cg(B, R, lam=15.0, tol=1e-8)
         ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12
-        for mode, name in ((0, "sharded"), (1, "replicated")):   # CG vectors sharded over the unknowns / replicated
+        modes = [(0, "sharded"), (1, "replicated")] + ([(3, "sharded_split_allgather")] if R == 32 else [])
+        for mode, name in modes:   # CG vectors sharded over the unknowns / replicated / sharded with the column-half all-gather
             fs.check(fs.lib().fsb_tune_cg_dist(mode))
             Xs, its = shard.cg(B, R, lam=15.0, tol=1e-8)
             out[f"{tag}_cg_{name}_iters"] = [itf, its]
