@@ -180,10 +180,15 @@ def run_ours(args):
     k = torch.arange(R, device="cuda", dtype=torch.float64)[None, :]
     X = torch.sin(7.0 * c + 17.0 * k + 0.3).reshape(-1).contiguous()
     Y = torch.empty(nrow * R, dtype=torch.float64, device="cuda")
-    if args.tune:
-        algo, tw, g, vec, slabs, rb = (int(v) for v in args.tune.split(","))
+    pinned = None
+    if args.tune:      # pin the launch configuration instead of the per-handle autotune (profiling runs)
+        vals = [int(v) for v in args.tune.split(",")]
+        algo, tw, g, vec, slabs, rb = vals[:6]
+        deep = vals[6] if len(vals) > 6 else 0
         fs.check(fs.lib().fsb_tune_csr_algo(algo, rb, 0))
         fs.check(fs.lib().fsb_tune_csr_spmm(tw, g, vec, slabs))
+        fs.check(fs.lib().fsb_tune_csr_staged(deep))
+        pinned = (R, max(slabs, 1), bool(deep))
 
     def barrier():
         if world > 1:
@@ -205,7 +210,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = fs.launch_count() - l0
-    tuned = A.tuning()
+    tuned = pinned or A.tuning()
     clocks = sampler.stop() if sampler else None
     ms = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
@@ -286,7 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--tune", default="", help="algo,tw,g,vec,slabs,rb override of the SpMM launch heuristic (see tools/sweep.py)")
+    ap.add_argument("--tune", default="", help="algo,tw,g,vec,slabs,rb[,deep] override of the SpMM launch heuristic (see tools/sweep.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,25 +4,28 @@
 // generalises the latter to R <= 32 right-hand sides (the reference hard-codes the
 // 2x2 solves; here alpha and psi come from an R x R Cholesky solve on the device).
 // Every vector stays in HBM for the whole solve; the iteration is predicated on device-side
-// status words, and the host reads them back once per batch of queued iterations.  With a row-sharded A and an active
-// communicator the partial A'(A P) is sum-allreduced inside fsb_ata_*; the dense
-// vectors are replicated and the Gram reductions are deterministic, so all ranks
-// take identical branches without exchanging the flags.
+// status words, and the host reads them back once per batch of queued iterations.
+// Two multi-GPU forms (row-sharded A, active communicator):
+//   * cg_run on replicated vectors: the partial A'(A P) is sum-allreduced inside fsb_ata_*;
+//   * cg_run_sharded (default): vectors sharded over the unknowns, reduce-scatter of the partial
+//     overlapped with its computation, all-gather of P, allreduce of the R x R Gram matrices.
+// The Gram reductions are deterministic and allreduced to identical bits, so all ranks take
+// identical branches without exchanging the flags.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
-#include <chrono>
-
 #include <algorithm>
+#include <chrono>
 
 #include "fsb_dense.h"
 #include "fsb_internal.h"
 
 namespace {
 
-// FSB_CG_TRACE=1: wall-clock milliseconds of the solve's phases on stderr (allocation, set-up, every
-// status read-back) -- a debugging aid for gaps the kernel timings do not show
+// FSB_CG_TRACE=1: wall-clock milliseconds of the solve's phases on stderr (workspace, every status
+// read-back); =2 adds the device time of the phases of a sharded iteration -- a debugging aid for
+// gaps the kernel timings do not show
 int cg_trace_level() {
   static const int lvl = [] { const char* e = getenv("FSB_CG_TRACE"); return e && *e ? atoi(e) : 0; }();
   return lvl;
@@ -148,7 +151,7 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
 // The F rows are cut into C chunks of Fc rows, every chunk into G slices of s rows; rank g owns slice g
 // of every chunk (local layout [C][s][R]).  The dense passes are row-local, so the layout is invisible
 // to them.  Rows are padded with zeros to C*G*s.
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 4;
 // 0 (and 2) = sharded vectors, 1 = replicated vectors + one allreduce,
 // 3 = sharded vectors with P all-gathered as two column halves behind the next product's first pass
 int g_cg_dist_mode = 0;
@@ -162,7 +165,7 @@ struct CgShardWork {
   double *partial = nullptr;
   int *status = nullptr, *h_status = nullptr;
   cudaStream_t comm_st = nullptr;
-  cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_lo = nullptr, ev_hi = nullptr;
   void release() {
     cudaFree(Psend);
@@ -184,7 +187,7 @@ void shard_layout(long F, int R, int G, int* C, long* s, long* Fc, long* Fp, lon
   // (four chunks: eight shorten the exposed tail -- the last chunk's reduce-scatter -- from 0.17 to 0.14 ms
   // on 8 GPUs at C5 but the smaller product launches lose 0.2 ms, profiles/r1i_cg_trace_n8_8chunks.log)
   (void)G;
-  *C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? 4 : 1;
+  *C = (R >= 2 && (double)F * R * 8.0 >= 32e6) ? kMaxChunks : 1;
   *s = (F + (long)*C * G - 1) / ((long)*C * G);
   if ((*s * R) % 2) *s += 1;            // keep every slice 16-byte aligned for the vector paths
   *Fc = *s * G; *Fp = *Fc * *C; *nloc = *s * *C;
@@ -237,7 +240,6 @@ int shard_allgather(CgShardWork& w, double* full, const double* loc, int R, cuda
   return rc != FSB_OK ? rc : rc2;
 }
 
-// KP_loc = slice of sum_g A_g'(A_g P) + lambda P_loc
 // all-gather of the new P as two column halves on the second stream, so that the first column pass of
 // the next A_g P starts as soon as the first half has arrived (the second half travels behind it)
 int shard_allgather_halves(CgShardWork& w, int R, cudaStream_t st) {
@@ -260,6 +262,7 @@ int shard_allgather_halves(CgShardWork& w, int R, cudaStream_t st) {
   return FSB_OK;
 }
 
+// KP_loc = slice of sum_g A_g'(A_g P) + lambda P_loc
 int shard_apply_op(fsb_matrix* A, fsb_matrix* Acsr, fsb_matrix* T, CgShardWork& w, int R, double lambda, cudaStream_t st, bool halves,
                    cudaEvent_t* trace = nullptr) {
   if (halves) {   // P arrived as column halves (shard_allgather_halves): one column pass per half
