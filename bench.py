@@ -139,7 +139,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     nrow, ncol, nnz, R, dist, seed = WORKLOADS[args.workload]
-    sample_rows = min(nrow, 1_000_000)
+    sample_rows = min(nrow, args.sample_rows)
     dt, snnz, kind, cores = cpu_time_steps(ncol, R, seed, sample_rows, nnz / nrow, args.steps, args.warmup)
     value = snnz * R / dt
     sample = f"{sample_rows} rows x {ncol} cols, {snnz} nnz of the {args.workload} matrix (same row degree, full X), per step"
@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--tune", default="", help="algo,tw,g,vec,slabs,rb[,deep] override of the SpMM launch heuristic (see tools/sweep.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sample-rows", type=int, default=1_000_000, help="--impl reference: rows of the workload each CPU step processes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
