@@ -151,6 +151,8 @@ int fsb_csr_upload(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* r
   int rc = upload_array(&A->row_ptr, row_ptr, (size_t)nrow + 1, g_stream);
   if (rc == FSB_OK) rc = upload_array(&A->cols, cols, (size_t)nnz, g_stream);
   if (rc == FSB_OK && vals) rc = upload_array(&A->vals, vals, (size_t)nnz, g_stream);
+  if (rc == FSB_OK) rc = fsb_check_row_ptr(A->row_ptr, (long)nrow + 1, nnz, "row_ptr", g_stream);
+  if (rc == FSB_OK) rc = fsb_check_index_range(A->cols, nnz, ncol, "column index", g_stream);
   if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
   if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
   A->bytes = ((size_t)nrow + 1) * 4 + (size_t)nnz * (vals ? 12 : 4);
@@ -192,6 +194,8 @@ int fsb_cbcsr_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, int col
   A->avg_row_nnz = nrow > 0 ? (double)nnz / nrow : 0.0;
   int rc = upload_array(&A->row_ptr, row_ptr, ncell + 1, g_stream);
   if (rc == FSB_OK) rc = upload_array(&A->cols, cols, (size_t)nnz, g_stream);
+  if (rc == FSB_OK) rc = fsb_check_row_ptr(A->row_ptr, (long)ncell + 1, nnz, "row_ptr", g_stream);
+  if (rc == FSB_OK) rc = fsb_check_index_range(A->cols, nnz, ncol, "column index", g_stream);
   if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
   if (rc != FSB_OK) { free_arrays(A); delete A; return rc; }
   A->bytes = (ncell + 1) * 4 + (size_t)nnz * 4;
@@ -228,6 +232,8 @@ int fsb_blocked_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, const
     if (e == cudaSuccess && vals) e = cudaMemcpyAsync(A->b_vals + off[b], vals[b], m * 8, cudaMemcpyHostToDevice, g_stream);
     if (e != cudaSuccess) rc = fsb_cuda_error(e, "blocked upload", __FILE__, __LINE__);
   }
+  if (rc == FSB_OK) rc = fsb_check_index_range(A->b_rows, A->nnz, nrow, "row index", g_stream);
+  if (rc == FSB_OK) rc = fsb_check_index_range(A->b_cols, A->nnz, ncol, "column index", g_stream);
   if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
   A->bytes = ((size_t)nblocks + 1) * 12 + n1 * (vals ? 16 : 8);
   if (rc == FSB_OK) rc = fsb_blocked_relayout(A, g_stream);

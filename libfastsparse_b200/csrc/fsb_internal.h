@@ -115,6 +115,9 @@ int fsb_launch_cbcsr_spmm(const fsb_matrix* A, double* dY, const double* dX, int
 int fsb_launch_blocked_spmm(const fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st);
 
 // ---- kernels_build.cu
+// input validation on the device (an out-of-range index would be an illegal address in the products)
+int fsb_check_index_range(const int* d_idx, long n, int limit, const char* what, cudaStream_t st);
+int fsb_check_row_ptr(const int* d_ptr, long n, long last, const char* what, cudaStream_t st);
 int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
                                const int* d_cols, const double* d_vals, cudaStream_t st);
 int fsb_build_transpose(fsb_matrix* A, cudaStream_t st);   // fills A->T

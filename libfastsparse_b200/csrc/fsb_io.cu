@@ -153,11 +153,9 @@ int fsb_csr_load_bin_file(fsb_matrix_t* out, const char* path, void* struct_imag
   }
   if (rc == FSB_OK) rc = file_to_device(fc.f, A->cols, (size_t)img.nnz * 4, p, st, "cols data corrupted");
   if (rc == FSB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "load sync", __FILE__, __LINE__);
-  if (rc == FSB_OK) {   // the same consistency check fsb_csr_upload applies to host arrays
-    int last = 0;
-    if (cudaMemcpy(&last, A->row_ptr + img.nrow, 4, cudaMemcpyDeviceToHost) != cudaSuccess || last != img.nnz)
-      rc = fsb_set_error(FSB_EIO, "ERROR: could not read data from file, row_ptr[nrow]=%d but nnz=%ld", last, img.nnz);
-  }
+  // the same consistency checks fsb_csr_upload applies: a corrupt file must not become an illegal device address
+  if (rc == FSB_OK) rc = fsb_check_row_ptr(A->row_ptr, (long)img.nrow + 1, img.nnz, "row_ptr", st);
+  if (rc == FSB_OK) rc = fsb_check_index_range(A->cols, img.nnz, img.ncol, "column index", st);
   if (rc != FSB_OK) { fsb_matrix_free(A); return rc; }
   A->bytes = ((size_t)img.nrow + 1) * 4 + (size_t)img.nnz * 4;
   *out = A;

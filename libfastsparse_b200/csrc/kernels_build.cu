@@ -74,6 +74,78 @@ int bits_for(int n) { int b = 1; while (b < 31 && (1LL << b) < n) ++b; return b;
 
 }  // namespace
 
+// ---- input validation.  The reference trusts its indices (an out-of-range one is undefined behaviour
+// on the CPU); on the GPU it would be an illegal address that poisons the whole context, so every
+// upload path checks its index arrays once, on the device, before the first product.
+namespace {
+__global__ void index_range_kernel(const int* __restrict__ a, long long n, int* __restrict__ minmax) {
+  int lo = INT_MAX, hi = INT_MIN;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { const int v = a[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+}
+// non-decreasing, first entry `first`, last entry `last`: flags[0] counts violations
+__global__ void monotone_kernel(const int* __restrict__ p, long long n, int first, int last, int* __restrict__ flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (; i < n; i += stride) {
+    const int v = p[i];
+    if (i == 0 && v != first) bad = 1;
+    if (i == n - 1 && v != last) bad = 1;
+    if (i + 1 < n && p[i + 1] < v) bad = 1;
+  }
+  if (bad) atomicAdd(flag, 1);
+}
+}  // namespace
+
+// all of d_idx[0..n) in [0, limit)?  `what` names the array in the error message
+int fsb_check_index_range(const int* d_idx, long n, int limit, const char* what, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  int* d = nullptr;
+  FSB_CUDA(cudaMalloc(&d, 2 * sizeof(int)));
+  const int init[2] = {INT_MAX, INT_MIN};
+  int h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(d, init, sizeof init, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    index_range_kernel<<<grid_for(n), 256, 0, st>>>(d_idx, n, d);
+    fsb_count_launch();
+    e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fsb_cuda_error(e, "index validation", __FILE__, __LINE__);
+  if (h[0] < 0 || h[1] >= limit)
+    return fsb_set_error(FSB_EINVAL, "%s out of range: found [%d, %d], valid is [0, %d)", what, h[0], h[1], limit);
+  return FSB_OK;
+}
+
+// d_ptr[0..n) non-decreasing with d_ptr[0] == 0 and d_ptr[n-1] == last?
+int fsb_check_row_ptr(const int* d_ptr, long n, long last, const char* what, cudaStream_t st) {
+  if (last > INT_MAX) return fsb_set_error(FSB_EINVAL, "%ld entries do not fit the int32 offsets of %s (the reference's struct layout)", last, what);
+  if (n <= 0) return FSB_OK;
+  int* d = nullptr;
+  FSB_CUDA(cudaMalloc(&d, sizeof(int)));
+  int h = 0;
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    monotone_kernel<<<grid_for(n), 256, 0, st>>>(d_ptr, n, 0, (int)last, d);
+    fsb_count_launch();
+    e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fsb_cuda_error(e, "row_ptr validation", __FILE__, __LINE__);
+  if (h) return fsb_set_error(FSB_EINVAL, "%s is not a valid offset array (must start at 0, never decrease and end at %ld)", what, last);
+  return FSB_OK;
+}
+
 // Sort (key, payload...) stably by key in [0, nkeys) and emit CSR arrays.
 static int coo_to_csr_dev(fsb_matrix* out, int nkeys, int nother, long nnz, const int* d_keys,
                           const int* d_other, const double* d_vals, cudaStream_t st) {
@@ -92,6 +164,8 @@ static int coo_to_csr_dev(fsb_matrix* out, int nkeys, int nother, long nnz, cons
     FSB_CUDA(cudaMemsetAsync(out->row_ptr, 0, ((size_t)nkeys + 1) * sizeof(int), st));
     return FSB_OK;
   }
+  FSB_TRY(fsb_check_index_range(d_keys, nnz, nkeys, "row index", st));
+  FSB_TRY(fsb_check_index_range(d_other, nnz, nother, "column index", st));
   int *keys_sorted = nullptr, *perm_in = nullptr, *perm_out = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0;

@@ -450,6 +450,40 @@ def test_noise_rhs_and_sampling_step():
     assert not torch.equal(A.noise_rhs(R, lam, seed + 1), Bm)    # a new seed is a new sample
 
 
+def test_invalid_indices_are_rejected_at_upload(tmp_path):
+    """The reference trusts its indices; on the GPU an out-of-range one would be an illegal address that kills the
+    context, so every upload / load path validates once on the device and fails with an error instead."""
+    nrow, ncol, nnz = 50, 20, 200
+    rng = np.random.default_rng(3)
+    rows = np.sort(rng.integers(0, nrow, nnz)).astype(np.int32); cols = rng.integers(0, ncol, nnz).astype(np.int32)
+    good = fs.new_bcsr(nnz, nrow, ncol, rows, cols)
+    x = tvec(ncol); y = np.zeros(nrow)
+
+    def expect_rejected(fn):
+        with pytest.raises(fs.FsbError) as e:
+            fn()
+        assert "out of range" in str(e.value) or "offset array" in str(e.value), str(e.value)
+
+    for bad_col in (ncol, -1, 2 ** 30):
+        c = good.cols.copy(); c[17] = bad_col
+        expect_rejected(lambda: fs.bcsr_A_mul_B(y, fs.BinaryCSR(nrow, ncol, good.row_ptr, c), x))
+    rp = good.row_ptr.copy(); rp[10] = rp[12] + 3              # a decreasing step
+    expect_rejected(lambda: fs.bcsr_A_mul_B(y, fs.BinaryCSR(nrow, ncol, rp, good.cols), x))
+    r = rows.copy(); r[5] = nrow                              # COO with a row index one past the end
+    expect_rejected(lambda: fs.A_mul_B(y, fs.SparseBinaryMatrix(nrow, ncol, r, cols), x))
+    # a .csr.bin whose column array was corrupted on disk
+    path = str(tmp_path / "m.csr.bin")
+    fs.serialize_to_file(good, path)
+    raw = bytearray(open(path, "rb").read())
+    raw[-4:] = np.array([ncol + 5], dtype=np.int32).tobytes()
+    open(path, "wb").write(bytes(raw))
+    expect_rejected(lambda: fs.DeviceMatrix.load_csr_bin(path))
+    # the context is still healthy
+    fs.bcsr_A_mul_B(y, good, x)
+    want = np.zeros(nrow); np.add.at(want, rows, x[cols])
+    assert np.max(np.abs(y - want)) < 1e-12
+
+
 def _write_coo_file(path, nrow, ncol, rows, cols, vals=None):
     """The reference's raw COO format (sparse.h:112-139, dsparse.h:64-93): 3 x int64, 1-based int32 indices."""
     with open(path, "wb") as f:
