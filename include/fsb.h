@@ -17,7 +17,10 @@
  *  - *_host entry points take HOST pointers (they copy X in and Y out: the
  *    drop-in path); *_dev entry points take DEVICE pointers, are asynchronous
  *    on `stream` (a cudaStream_t passed as void*, NULL = the library's stream)
- *    and never touch the host;
+ *    and never touch the host -- with two documented exceptions: the first
+ *    multi-RHS product on a large handle times its launch candidates (it
+ *    synchronises once, see fsb_matrix_tuning), and the solver reads three
+ *    status words back per batch of iterations;
  *  - outputs are fully overwritten (alpha = 1, beta = 0), like the reference;
  *  - there is NO CPU fallback: without a CUDA device every compute call fails
  *    with FSB_ENODEV.  The fsb_host_* functions are the reference's host-side
@@ -59,6 +62,10 @@ void* fsb_stream(void);                  /* the library's cudaStream_t      */
 long fsb_launch_count(void);
 
 /* ------------------------------------------------- upload (host -> HBM) */
+/* Every upload / load path validates its index arrays once on the device (0 <= index < dimension,
+ * offsets non-decreasing from 0 to nnz, nnz < 2^31) and returns FSB_EINVAL on a violation: an
+ * out-of-range index -- undefined behaviour in the reference -- would otherwise be an illegal
+ * device address. */
 /* CSR, binary when vals == NULL.  Replaces the storage side of new_bcsr
  * (csr.h:30-67) / new_csr (csr.h:375-422): arrays are copied verbatim, so
  * row order, in-row order and duplicates are exactly the host structure's. */
