@@ -44,6 +44,19 @@ constexpr int kLongRow = 2048;   // rows at least this long are split across the
 #ifndef FSB_STAGED_DEEP_MINB
 #define FSB_STAGED_DEEP_MINB 4
 #endif
+#ifndef FSB_STAGED_DEEP_MINB_VALS      // matrices with values carry U more doubles per batch
+#define FSB_STAGED_DEEP_MINB_VALS 4
+#endif
+// FSB_STAGED_TMA 1 (default): the contiguous run of column indices of a CTA's rows is brought into shared
+// memory by one TMA bulk copy (cp.async.bulk, SASS UBLKCP, completion on an mbarrier) instead of
+// per-thread coalesced loads + shared stores.  The run starts at an arbitrary entry, so the copy starts
+// at the enclosing 16-byte boundary and the indices are read at a shift of 0..3 entries.  Same box, C2:
+// 5.15 -> 5.05 ms (deep, two passes), 5.44 -> 5.09 ms (lean, two passes); C4 3.08 -> 2.95 ms; R = 8
+// 1.08 -> 1.03 ms (profiles/r1k_sweep_tma_staging.md).  Matrices with values keep the per-thread
+// staging: with a second bulk copy the deep build spills and loses 4 %.
+#ifndef FSB_STAGED_TMA
+#define FSB_STAGED_TMA 1
+#endif
 
 // Empty volatile asm that takes a loaded row piece in and out: volatile asms keep their order, so
 // placing these after the U gather asms keeps "all U loads, then the adds" in the emitted code.
@@ -106,7 +119,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   int* s_rp = reinterpret_cast<int*>(smem_raw);
   unsigned char* body = smem_raw + (((size_t)(RB + 1) * 4 + 15) & ~(size_t)15);
   double* s_vals = reinterpret_cast<double*>(body);
-  int* s_cols = reinterpret_cast<int*>(body + (VALS ? (size_t)CAP * 8 : 0));
+  int* s_cols = reinterpret_cast<int*>(body + (VALS ? (size_t)(CAP + 8) * 8 : 0));
   double* s_red = reinterpret_cast<double*>(body);
 
   constexpr int NT = kThreads / G;   // sub-groups per CTA
@@ -121,22 +134,41 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
 
+  constexpr bool kTma = FSB_STAGED_TMA && !VALS;
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (kTma && tid == 0) mbar_init(&s_bar, 1);
   for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptr + r0 + i);
   __syncthreads();
   const int base = s_rp[0];
   const int total = s_rp[nr] - base;
 
   if (total <= CAP) {
-    for (int i = tid; i < total; i += kThreads) {
-      s_cols[i] = ld_stream_s32_pol(cols + base + i, spol);
-      if (VALS) s_vals[i] = ld_stream_f64_pol(vals + base + i, spol);
+    const int* ci = s_cols;
+    const double* vi = s_vals;
+    if constexpr (kTma) {
+      // one bulk copy from the enclosing 16-byte boundary (the buffer has 8 entries of slack for that)
+      const int shc = base & 3;
+      if (total > 0) {
+        if (tid == 0) {
+          const unsigned bytes = (unsigned)((shc + total + 3) & ~3) * 4u;
+          mbar_expect_tx(&s_bar, bytes);
+          tma_load_1d(s_cols, cols + (base - shc), bytes, &s_bar, spol);
+        }
+        mbar_wait(&s_bar, 0);
+      }
+      ci = s_cols + shc;
+    } else {
+      for (int i = tid; i < total; i += kThreads) {
+        s_cols[i] = ld_stream_s32_pol(cols + base + i, spol);
+        if (VALS) s_vals[i] = ld_stream_f64_pol(vals + base + i, spol);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     for (int r = team; r < nr; r += NT) {
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true, DEEP>(s_cols, s_vals, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol);
+      walk_row<G, VEC, VALS, true, DEEP>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -197,7 +229,7 @@ csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __r
 }
 
 template <int G, int VEC, bool VALS>
-__global__ void __launch_bounds__(kThreads, FSB_STAGED_DEEP_MINB)
+__global__ void __launch_bounds__(kThreads, VALS ? FSB_STAGED_DEEP_MINB_VALS : FSB_STAGED_DEEP_MINB)
 csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                             int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
@@ -211,7 +243,7 @@ template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
            const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
   auto kern = deep ? csr_spmm_staged_deep_kernel<G, VEC, VALS> : csr_spmm_staged_kernel<G, VEC, VALS>;
-  size_t body = std::max((size_t)CAP * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging or long-row reduction
+  size_t body = std::max((size_t)(CAP + 8) * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging (+ alignment slack) or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
