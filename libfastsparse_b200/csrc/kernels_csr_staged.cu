@@ -57,6 +57,10 @@ constexpr int kLongRow = 2048;   // rows at least this long are split across the
 #ifndef FSB_STAGED_TMA
 #define FSB_STAGED_TMA 1
 #endif
+// experiment: matrices with values bring their indices by TMA too (the values stay per-thread loads)
+#ifndef FSB_STAGED_TMA_VALS
+#define FSB_STAGED_TMA_VALS 0
+#endif
 
 // Empty volatile asm that takes a loaded row piece in and out: volatile asms keep their order, so
 // placing these after the U gather asms keeps "all U loads, then the adds" in the emitted code.
@@ -134,7 +138,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
 
-  constexpr bool kTma = FSB_STAGED_TMA && !VALS;
+  constexpr bool kTma = FSB_STAGED_TMA && (!VALS || FSB_STAGED_TMA_VALS);
   __shared__ __align__(8) unsigned long long s_bar;
   if (kTma && tid == 0) mbar_init(&s_bar, 1);
   for (int i = tid; i <= nr; i += kThreads) s_rp[i] = __ldg(row_ptr + r0 + i);
@@ -153,6 +157,10 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
           const unsigned bytes = (unsigned)((shc + total + 3) & ~3) * 4u;
           mbar_expect_tx(&s_bar, bytes);
           tma_load_1d(s_cols, cols + (base - shc), bytes, &s_bar, spol);
+        }
+        if (VALS) {   // values by per-thread streaming loads while the bulk copy is in flight
+          for (int i = tid; i < total; i += kThreads) s_vals[i] = ld_stream_f64_pol(vals + base + i, spol);
+          __syncthreads();
         }
         mbar_wait(&s_bar, 0);
       }
