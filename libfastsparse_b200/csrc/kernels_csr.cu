@@ -335,18 +335,25 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   if (R <= 0) return fsb_set_error(FSB_EINVAL, "spmm: R must be positive (got %d)", R);
   if (A->nrow == 0) return FSB_OK;
   const uintptr_t al = (uintptr_t)dX | (uintptr_t)dY | (uintptr_t)dZ;
-  // ---- one right-hand side: the product is bound by the L1 sector-gather rate of x (200 M random
-  // 8-byte gathers), so the kernel with the least overhead wins when rows are regular: the
-  // team-per-row kernel.  Skewed matrices (a row far longer than the mean, e.g. transposes of
-  // power-law matrices) go to the entry-balanced merge-path stream kernel (230 ms -> 1.9 ms).
+  // ---- one right-hand side: x is L2-resident and every entry is one random 8-byte gather, so the product is
+  // bound by the L1TEX / L2 request rate; what differs between the kernels is the overhead around the gathers
+  // (profiles/r1m_sweep_spmv.md):
+  //  * binary, short regular rows: the staged row-block kernel with two lanes per row (the second lane idles):
+  //    0.75 ms at C3's structure against 0.91 ms for the team-per-row kernel and 0.90 ms for the stream kernel;
+  //  * binary, long regular rows (transposes: 200 entries per row): a warp per row, 1.02 ms against 1.28 ms (stream);
+  //  * matrices with values: the entry-balanced merge-path stream kernel, 1.08 / 1.29 ms (A / A') against
+  //    1.13 / 1.40 ms for the team-per-row kernel;
+  //  * skewed rows (a row far longer than the mean, e.g. transposes of power-law matrices): the stream kernel
+  //    whatever the values (230 ms -> 1.9 ms).
   if (R == 1 && (g_algo == 0 || g_algo == 3)) {
-    bool stream = g_algo == 3;
+    bool stream = g_algo == 3 || A->has_vals;
     if (!stream) {
       int mx = 0;
       FSB_TRY(max_row_nnz(A, st, &mx));
       stream = mx > std::max(4096.0, 64.0 * A->avg_row_nnz);
     }
     if (stream) return stream_config(A, dY, dX, R, st, dZ, lambda);
+    if (A->avg_row_nnz <= 48.0) return run_config(A, dY, dX, 1, 2, 1, 1, 2, g_tw, st, dZ, lambda, false);
     return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st, dZ, lambda);
   }
   if (g_algo == 3 && fsb_csr_stream_supports(R)) return stream_config(A, dY, dX, R, st, dZ, lambda);
