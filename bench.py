@@ -138,6 +138,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # The reference arm uses every host thread it can: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would silently time the reference's OpenMP loops on one core.  Set before the OpenMP runtime is loaded.
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("FSB_REF_THREADS", str(usable))
     nrow, ncol, nnz, R, dist, seed = WORKLOADS[args.workload]
     sample_rows = min(nrow, args.sample_rows)
     dt, snnz, kind, cores = cpu_time_steps(ncol, R, seed, sample_rows, nnz / nrow, args.steps, args.warmup)

@@ -26,6 +26,18 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in line["config"] and "model" not in line["config"]
 
 
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must still use every usable core."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2", "--workload", "c2_small", "--steps", "1", "--warmup", "1",
+                        "--sample-rows", "20000"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    usable = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == usable, (line["cpu_baseline"], usable)
+    assert line["n_gpus"] == 2
+
+
 def test_non_zero_ranks_of_the_reference_arm_do_nothing():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
