@@ -17,6 +17,8 @@
 //     own order: the binary product is bit-identical to the serial reference;
 //   * rows too long for the staging buffer are processed by the whole CTA (fixed
 //     chunking + shared-memory reduction, still deterministic).
+#include <stdint.h>
+
 #include <algorithm>
 
 #include "fsb_device.cuh"
@@ -251,6 +253,10 @@ int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
            const double* dZ, double lambda, bool deep, int ldx, int xcol0) {
+  // the TMA staging copies from the 16-byte boundary below a row's first entry: the index array itself must sit on one
+  // (every array the library allocates does)
+  if (FSB_STAGED_TMA && (!VALS || FSB_STAGED_TMA_VALS) && ((uintptr_t)A->cols & 15))
+    return fsb_set_error(FSB_EINVAL, "staged SpMM: column index array is not 16-byte aligned");
   auto kern = deep ? csr_spmm_staged_deep_kernel<G, VEC, VALS> : csr_spmm_staged_kernel<G, VEC, VALS>;
   size_t body = std::max((size_t)(CAP + 8) * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging (+ alignment slack) or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
