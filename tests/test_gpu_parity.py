@@ -573,6 +573,51 @@ def test_full_size_c2_properties():
     assert torch.allclose(lhs, rhs, rtol=1e-10)
 
 
+def test_full_size_c3_c4_c5_properties():
+    """The other BASELINE.json configs at full size through size-independent properties.
+    C3 (double CSR 10M x 1M, 200M nnz): entry-sum identity sum_r y[r] == sum_j vals[j] x[cols[j]], a row slab against
+    the oracle, the adjoint identity <A x, u> == <x, A'u>.  C4 (power-law columns, R = 32): the blocked (Hilbert) and
+    column-blocked formats against CSR on the same entries.  C5: the block-CG solve on the C2 matrix reaches its tolerance
+    (residual recomputed with the product kernels)."""
+    import torch
+    N, F, NNZ = 10_000_000, 1_000_000, 200_000_000
+    # ---- C3
+    A = fs.DeviceMatrix.synth(0x5EED0003, 0, NNZ, N, F, with_vals=True, keep_coo=True)
+    _, cols_t, vals_t = A.coo
+    x = (torch.sin(7.0 * torch.arange(F, device="cuda", dtype=torch.float64) + 0.3) / 10).contiguous()
+    y = A.spmm(x, 1)
+    entry_sum = float((vals_t * x[cols_t.long()]).sum())
+    del A.coo, cols_t, vals_t
+    assert abs(float(y.sum()) - entry_sum) <= 1e-11 * NNZ * 0.1            # |terms| <= 0.1
+    S = A.row_slice(0, 3000); rp, cc, vv = S.download_csr()
+    want = oracle.csr_mul(3000, rp, cc, vv, x.cpu().numpy().reshape(F, 1), 1)
+    assert_close(y[:3000].cpu().numpy(), want, 8.0, what="C3 row slab")
+    u = torch.cos(3.0 * torch.arange(N, device="cuda", dtype=torch.float64)).contiguous()
+    z = A.spmm_t(u, 1)
+    lhs, rhs = float((y * u).sum()), float((x * z).sum())
+    assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs), float(y.abs().sum()))
+    A.free(); del A, y, z, u, S
+    # ---- C4
+    R = 32
+    M = fs.DeviceMatrix.synth(0x5EED0004, 1, NNZ, N, F, keep_coo=True)
+    rows_t, cols_t, _ = M.coo
+    X = torch.randn(F * R, dtype=torch.float64, device="cuda")
+    Y = M.spmm(X, R)
+    Bk = fs.DeviceMatrix.blocked_from_coo_tensors(N, F, rows_t, cols_t, None, 512, order=1)
+    assert float((Bk.spmm(X, R) - Y).abs().max()) <= 1e-12 * 4.0 * 4096
+    Bk.free(); del Bk
+    Cb = fs.DeviceMatrix.cbcsr_from_coo_tensors(N, F, rows_t, cols_t, 65536)
+    assert float((Cb.spmm(X, R) - Y).abs().max()) <= 1e-12 * 4.0 * 4096
+    Cb.free(); del Cb, M.coo, rows_t, cols_t
+    M.free(); del M, X, Y
+    # ---- C5
+    K = fs.DeviceMatrix.synth(0x5EED0002, 0, NNZ, N, F)
+    Bm = K.noise_rhs(R, 15.0, 7)
+    Xs, it = K.cg(Bm, R, lam=15.0, tol=1e-6)
+    res = (K.ata(Xs, R, lam=15.0) - Bm).reshape(F, R).norm(dim=0) / Bm.reshape(F, R).norm(dim=0)
+    assert 5 <= it <= 30 and float(res.max()) < 2e-6
+
+
 # ------------------------------------------------------------------ device-side builders of the blocked formats (SURVEY 8f)
 @pytest.mark.parametrize("bs", [64, 512])
 @pytest.mark.parametrize("with_vals", [False, True])
