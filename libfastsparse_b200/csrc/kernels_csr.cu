@@ -6,7 +6,13 @@
 //   csr_A_mul_B csr.h:425-438, csr_A_mul_Bn csr.h:441-465,
 //   bcsr_AA_mul_B / parallel_bcsr_AA_mul_B csr.h:305-355 (fused mode).
 //
-// Design (not a port: the reference gives each CPU thread whole rows and a private
+// This file holds (i) the dispatch of every CSR product (fsb_launch_csr_spmm: which kernel, how many
+// column passes, which build -- partly decided by timing, once per handle), (ii) the first-generation
+// team-per-row kernel, still the choice for one right-hand side on binary matrices with long regular
+// rows, and (iii) the fused A'(A x) kernel.  The multi-RHS work horse is kernels_csr_staged.cu, the
+// entry-balanced SpMV kernel kernels_csr_stream.cu.
+//
+// Team-per-row design (not a port: the reference gives each CPU thread whole rows and a private
 // accumulator vector).  Here a TEAM of TW lanes owns one row.  The team streams the
 // row's column indices with one coalesced load per TW entries, then hands each index
 // to a SUB-GROUP of G lanes by warp shuffle; the G lanes gather G*VEC consecutive

@@ -6,9 +6,10 @@
 // loads (row_ptr -> cols -> X rows) and each team has little in flight
 // (profiles/r1a_ncu_c2_spmm_details.md).  This kernel breaks the chain:
 //
-//   * a CTA owns RB consecutive rows; it first copies their row_ptr slice and the whole
-//     contiguous run of column indices (and values) into SHARED MEMORY with fully
-//     coalesced loads -- one exposed latency per RB rows instead of per row;
+//   * a CTA owns RB consecutive rows; it first brings their row_ptr slice and the whole
+//     contiguous run of column indices (and values) into SHARED MEMORY -- the index run by one
+//     TMA bulk copy (cp.async.bulk + mbarrier; binary matrices), values by fully coalesced
+//     streaming loads -- one exposed latency per RB rows instead of per row;
 //   * then every sub-group of G lanes walks its rows with the indices already on chip:
 //     U independent gathers of the dense operand are issued back to back (each lane one
 //     vector LDG of VEC doubles; VEC = 4 is a single 256-bit LDG.E.256), so a warp keeps
@@ -16,7 +17,10 @@
 //   * a sub-group sums a row's terms strictly in stored order, i.e. in the reference's
 //     own order: the binary product is bit-identical to the serial reference;
 //   * rows too long for the staging buffer are processed by the whole CTA (fixed
-//     chunking + shared-memory reduction, still deterministic).
+//     chunking + shared-memory reduction, still deterministic);
+//   * two builds of the same body (lean: 32 registers, full occupancy; deep: all U gathers
+//     of a batch in flight) and one or two column passes are chosen per handle by timing
+//     (kernels_csr.cu); with two lanes per row it is also the binary SpMV kernel.
 #include <stdint.h>
 
 #include <algorithm>
