@@ -29,6 +29,12 @@
 
 namespace {
 
+// experiment knob: minimum resident CTAs per SM promised to ptxas for the Gram / row-mix kernels (1 = let it use
+// 150-200 registers, one CTA of 8 warps per SM; 2 = cap at 128 registers, which spills 100-470 bytes per thread
+// and measured 0.1-0.4 ms slower per C5 iteration)
+#ifndef FSB_DENSE_MINB
+#define FSB_DENSE_MINB 1
+#endif
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSms = 148;
@@ -119,7 +125,7 @@ __device__ __forceinline__ void reduce_gram_cta(double* red, const double (&acc)
 
 // partial[cta][R*R] = sum over this CTA's rows of Xa[i][a] * Xb[i][b]   (SYM: Xb == Xa)
 template <int NB, bool V32, bool SYM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FSB_DENSE_MINB)
 gram_partial_kernel(double* __restrict__ partial, const double* Xa, const double* Xb, long long n, int R) {
   __shared__ double red[4 * NB * 8 * NB * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -304,7 +310,7 @@ struct MixFrag {
 constexpr int kScratchStride = 36;   // doubles per scratch row: conflict-free fragment reads, 16-byte aligned rows
 
 template <int NB, bool V32, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FSB_DENSE_MINB)
 cg_mix_kernel(double* O, const double* I, const double* Add, const double* __restrict__ M, double* __restrict__ partial,
               long long n, int R, const int* __restrict__ status) {
   using F = MixFrag<NB, V32>;
