@@ -1,16 +1,15 @@
-/* utils.h -- drop-in for libfastsparse's utils.h (read_long, utils.h:4-12). */
-#ifndef UTILS_H
-#define UTILS_H
+/* utils.h -- drop-in for libfastsparse's utils.h: read_long (utils.h:4-12) forwards to the library. */
+#ifndef FSB_DROPIN_UTILS_H
+#define FSB_DROPIN_UTILS_H
 #include <stdio.h>
-#include <stdlib.h>
 
-/* one native 8-byte long from the stream; a short read is fatal, as in the reference */
+#include "../fsb.h"
+
+/* a short read is fatal, with the reference's message and exit code */
 static inline long read_long(FILE* fh) {
-  long value = 0;
-  if (fread(&value, sizeof value, 1, fh) != 1) {
-    fprintf(stderr, "File reading error for a long. File is corrupt.\n");
-    exit(1);
-  }
-  return value;
+  int ok = 0;
+  const long v = fsb_host_read_long(fh, &ok);
+  if (!ok) fsb_die("read_long");
+  return v;
 }
-#endif /* UTILS_H */
+#endif

@@ -242,6 +242,8 @@ int fsb_host_sort_coo_hilbert(int nrow, int ncol, long nnz, int* rows, int* cols
 int fsb_host_sort_block_hilbert(int start_row, int nrows_in_block, long nnz, int* rows,
                                 int* cols, double* vals);     /* sparse.h:215-236, dsparse.h:193-216 */
 int fsb_host_sort_block_byrow(int ncol, long nnz, int* rows, int* cols);  /* sparse.h:238-256 */
+/* one native 8-byte integer from an open FILE* (read_long utils.h:4-12); *ok = 0 on a short read */
+long fsb_host_read_long(void* file, int* ok);
 /* raw COO files (read_sbm sparse.h:112-139, read_sdm dsparse.h:64-93);
  * first call with rows == NULL returns the header */
 int fsb_host_read_coo(const char* path, long* nrow, long* ncol, long* nnz, int* rows,

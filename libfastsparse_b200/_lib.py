@@ -92,6 +92,7 @@ _SIGS = {
     "fsb_host_sort_coo_hilbert": (C.c_int, [C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
     "fsb_host_sort_block_hilbert": (C.c_int, [C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
     "fsb_host_sort_block_byrow": (C.c_int, [C.c_int, C.c_long, c_int_p, c_int_p]),
+    "fsb_host_read_long": (C.c_long, [C.c_void_p, c_int_p]),
     "fsb_host_read_coo": (C.c_int, [C.c_char_p, c_long_p, c_long_p, c_long_p, c_int_p, c_int_p, c_dbl_p]),
     "fsb_host_write_csr_bin": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_long, c_int_p, c_int_p]),
     "fsb_host_read_csr_bin": (C.c_int, [C.c_char_p, C.c_void_p, c_int_p, c_int_p]),

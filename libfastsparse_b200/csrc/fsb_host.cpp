@@ -228,6 +228,15 @@ int fsb_host_sort_block_byrow(int ncol, long nnz, int* rows, int* cols) {
 // ---------------------------------------------------------------- file formats
 // read_sbm sparse.h:112-139 / read_sdm dsparse.h:64-93: int64 nrow, ncol, nnz; int32
 // rows[nnz], cols[nnz] (1-based on disk); optional float64 vals[nnz]
+// one native 8-byte integer from an open stream (read_long utils.h:4-12); *ok = 0 on a short read
+long fsb_host_read_long(void* file, int* ok) {
+  int64_t v = 0;
+  const bool good = file && fread(&v, sizeof v, 1, static_cast<FILE*>(file)) == 1;
+  if (ok) *ok = good ? 1 : 0;
+  if (!good) fsb_set_error(FSB_EIO, "File reading error for a long. File is corrupt.");
+  return (long)v;
+}
+
 int fsb_host_read_coo(const char* path, long* nrow, long* ncol, long* nnz, int* rows, int* cols, double* vals) {
   FILE* f = fopen(path, "rb");
   if (!f) return fsb_set_error(FSB_EIO, "File error: %s", path ? path : "(null)");
