@@ -165,3 +165,21 @@ def test_synth_generator_host_is_deterministic_and_in_range():
     _, cz, _ = fs.synth_coo_host(0x5EED0004, 1, 200000, 1000, 4096)
     cnt = np.sort(np.bincount(cz, minlength=4096))[::-1]
     assert cz.min() >= 0 and cz.max() < 4096 and cnt[0] > 50 * max(1, cnt[2048])   # heavy head: power law
+
+
+def test_read_long_matches_reference_loader(tmp_path):     # utils.h:4-12
+    """read_long: one native 8-byte integer per call; a short read reports the reference's message."""
+    import ctypes as C
+    import numpy as np
+    L = fs.lib()
+    path = tmp_path / "longs.bin"
+    np.array([100, 50, 504], dtype=np.int64).tofile(path)
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p; libc.fopen.argtypes = [C.c_char_p, C.c_char_p]; libc.fclose.argtypes = [C.c_void_p]
+    f = libc.fopen(str(path).encode(), b"rb")
+    ok = C.c_int(0)
+    got = [L.fsb_host_read_long(f, C.byref(ok)) for _ in range(3)]
+    assert got == [100, 50, 504] and ok.value == 1
+    L.fsb_host_read_long(f, C.byref(ok))                    # past the end
+    assert ok.value == 0 and b"File is corrupt" in L.fsb_last_error()
+    libc.fclose(f)
