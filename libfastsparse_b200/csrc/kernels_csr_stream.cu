@@ -53,9 +53,12 @@ __global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restri
   split[b] = merge_search(row_ptr, nrow, nnz, d);
 }
 
-// (min 4 CTAs/SM: without it ptxas budgets 32 registers and serialises the PER independent loads)
-template <int RT, bool VALS>
-__global__ void __launch_bounds__(kThreads, 4)
+// MINB = minimum resident CTAs per SM promised to ptxas.  Without one it budgets 32 registers and serialises the PER
+// independent loads.  Two builds: 6 CTAs/SM (42 registers) is 11 % faster when the dense operand is small and mostly
+// hits in cache (C3 double SpMV, x = 8 MB: 0.97 vs 1.08 ms), 4 CTAs/SM (56 registers, all loads of a thread in flight)
+// is 13 % faster when it is large (the transpose, x = 80 MB: 1.31 vs 1.48 ms).  The launcher picks by operand size.
+template <int RT, bool VALS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                   const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                   const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {
@@ -199,7 +202,10 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
     FSB_KERNEL_CHECK();
     A->split_tile = kTile;
   }
-  csr_stream_kernel<RT, VALS><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
+  if ((double)A->ncol * RT * 8.0 <= 32e6)
+    csr_stream_kernel<RT, VALS, 6><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
+  else
+    csr_stream_kernel<RT, VALS, 4><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
   FSB_KERNEL_CHECK();
   csr_stream_fixup_kernel<RT><<<(ntiles + 255) / 256, 256, 0, st>>>(ntiles, carry_row, carry_val, dY);
   FSB_KERNEL_CHECK();
