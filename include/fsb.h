@@ -296,6 +296,11 @@ int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult);
  * ~3 gathers in flight per lane), 1 deep (half occupancy, 8 gathers in flight per lane) */
 int fsb_tune_csr_staged(int deep);
 
+/* Named experiment knobs (per calling thread, like every fsb_tune_* call; the environment variable
+ * FSB_TUNE_<NAME> gives the default).  Known knobs: "stream_policy" (1 = L2 evict_first on the matrix
+ * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads). */
+int fsb_tune(const char* knob, int value);
+
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable
  * CSR view of the same entries, built once on the device and cached in the handle;
  * native = 1: the format's own kernels (kernels_blocked.cu, kernels_cbcsr.cu). */

@@ -106,6 +106,7 @@ _SIGS = {
     "fsb_tune_csr_spmm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fsb_tune_csr_staged": (C.c_int, [C.c_int]),
     "fsb_tune_formats": (C.c_int, [C.c_int]),
+    "fsb_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "fsb_tune_cg_dist": (C.c_int, [C.c_int]),
     "fsb_tune_csr_algo": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fsb_synth_coo_dev": (C.c_int, [C.c_ulonglong, C.c_int, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

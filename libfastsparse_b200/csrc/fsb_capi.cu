@@ -22,7 +22,7 @@ int g_device = -1;
 cudaStream_t g_stream = nullptr;
 cudaStream_t g_copy_stream = nullptr;
 std::atomic<long> g_launches{0};
-int g_native_formats = 0;   // fsb_tune_formats: 1 = the blocked formats' own kernels, 0 = CSR view
+thread_local int g_native_formats = 0;   // fsb_tune_formats: 1 = the blocked formats' own kernels, 0 = CSR view
 }  // namespace
 
 int fsb_set_error(int code, const char* fmt, ...) {
@@ -37,6 +37,39 @@ int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line) 
   const char* base = strrchr(file, '/');
   return fsb_set_error(e == cudaErrorMemoryAllocation ? FSB_ENOMEM : FSB_ECUDA, "CUDA error %d (%s) in %s at %s:%d",
                        (int)e, cudaGetErrorString(e), what, base ? base + 1 : file, line);
+}
+
+// experiment knobs: a small per-thread name -> value table (fsb_tune), default from FSB_TUNE_<NAME> in the environment
+namespace {
+struct Knob { char name[32]; int value; };
+thread_local Knob tl_knobs[16];
+thread_local int tl_nknobs = 0;
+}  // namespace
+
+int fsb_knob(const char* name, int dflt) {
+  for (int i = 0; i < tl_nknobs; ++i)
+    if (!strcmp(tl_knobs[i].name, name)) return tl_knobs[i].value;
+  char env[64] = "FSB_TUNE_";
+  size_t k = strlen(env);
+  for (const char* p = name; *p && k + 1 < sizeof env; ++p) env[k++] = (*p >= 'a' && *p <= 'z') ? (char)(*p - 32) : *p;
+  env[k] = 0;
+  const char* e = getenv(env);
+  const int v = e ? atoi(e) : dflt;
+  if (tl_nknobs < 16) {   // remember (also caches the environment lookup)
+    snprintf(tl_knobs[tl_nknobs].name, sizeof tl_knobs[0].name, "%s", name);
+    tl_knobs[tl_nknobs++].value = v;
+  }
+  return v;
+}
+
+extern "C" int fsb_tune(const char* knob, int value) {
+  if (!knob || !*knob || strlen(knob) >= sizeof tl_knobs[0].name) return fsb_set_error(FSB_EINVAL, "fsb_tune: bad knob name");
+  for (int i = 0; i < tl_nknobs; ++i)
+    if (!strcmp(tl_knobs[i].name, knob)) { tl_knobs[i].value = value; return FSB_OK; }
+  if (tl_nknobs >= 16) return fsb_set_error(FSB_EINVAL, "fsb_tune: knob table full");
+  snprintf(tl_knobs[tl_nknobs].name, sizeof tl_knobs[0].name, "%s", knob);
+  tl_knobs[tl_nknobs++].value = value;
+  return FSB_OK;
 }
 
 void fsb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

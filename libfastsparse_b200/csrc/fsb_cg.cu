@@ -154,7 +154,7 @@ int cg_run(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, int R, d
 constexpr int kMaxChunks = 4;
 // 0 (and 2) = sharded vectors, 1 = replicated vectors + one allreduce,
 // 3 = sharded vectors with P all-gathered as two column halves behind the next product's first pass
-int g_cg_dist_mode = 0;
+thread_local int g_cg_dist_mode = 0;
 
 struct CgShardWork {
   int G = 1, rank = 0, C = 1;

@@ -56,6 +56,8 @@ int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 int fsb_require_device();
 cudaStream_t fsb_default_stream();
 void fsb_count_launch(int n = 1);
+// experiment knob (per calling thread; fsb_tune sets it, FSB_TUNE_<NAME> in the environment is the default)
+int fsb_knob(const char* name, int dflt);
 
 #define FSB_CUDA(call)                                                        \
   do {                                                                        \

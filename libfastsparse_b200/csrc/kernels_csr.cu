@@ -171,8 +171,10 @@ __global__ void scale_copy_kernel(double* __restrict__ Y, const double* __restri
   for (; i < n; i += stride) Y[i] = lambda * X[i];
 }
 
-int g_tw = 0, g_g = 0, g_vec = 0, g_slabs = 0;
-int g_algo = 0;   // 0 = automatic, 1 = team-per-row kernel (this file), 2 = staged row-block kernel,
+// tuning overrides are per calling thread (tools and tests set them on the thread that runs the products): a tuning
+// call from one thread never changes another thread's products (bench_a_mul_b.c:400-421 calls from two threads)
+thread_local int g_tw = 0, g_g = 0, g_vec = 0, g_slabs = 0;
+thread_local int g_algo = 0;   // 0 = automatic, 1 = team-per-row kernel (this file), 2 = staged row-block kernel,
                   // 3 = merge-path stream kernel where it applies (R = 1, 2, 4), staged otherwise
 
 inline int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -260,7 +262,7 @@ extern "C" int fsb_tune_csr_algo(int algo, int rows_per_cta, int cap_mult) {
   return FSB_OK;
 }
 
-int g_deep = -1;   // staged kernel build: -1 automatic (timed per handle), 0 lean, 1 deep
+thread_local int g_deep = -1;   // staged kernel build: -1 automatic (timed per handle), 0 lean, 1 deep
 
 extern "C" int fsb_tune_csr_staged(int deep) {
   if (deep < -1 || deep > 1) return fsb_set_error(FSB_EINVAL, "fsb_tune_csr_staged: deep must be -1, 0 or 1");

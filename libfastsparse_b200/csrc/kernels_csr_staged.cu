@@ -252,7 +252,7 @@ csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int
   staged_body<G, VEC, VALS, true>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0);
 }
 
-int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
+thread_local int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
 
 template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,

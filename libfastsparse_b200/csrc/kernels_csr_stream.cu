@@ -57,7 +57,10 @@ __global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restri
 // independent loads.  Two builds: 6 CTAs/SM (42 registers) is 11 % faster when the dense operand is small and mostly
 // hits in cache (C3 double SpMV, x = 8 MB: 0.97 vs 1.08 ms), 4 CTAs/SM (56 registers, all loads of a thread in flight)
 // is 13 % faster when it is large (the transpose, x = 80 MB: 1.31 vs 1.48 ms).  The launcher picks by operand size.
-template <int RT, bool VALS, int MINB>
+// POL: L2 cache-policy words on the loads -- the matrix stream (cols / vals, touched once) is marked evict_first and
+// the gathered dense operand evict_last, so a 2.4 GB matrix stream cannot push an 80 MB x (the transposed product
+// of C3) out of the 126 MB L2; the staged kernel has used the same words since round 1 (fsb_device.cuh).
+template <int RT, bool VALS, int MINB, bool POL>
 __global__ void __launch_bounds__(kThreads, MINB)
 csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                   const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
@@ -83,21 +86,29 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
     int c[PER];
     double v[PER];
     double xv[PER][RT];
+    unsigned long long pol_stream = 0, pol_keep = 0;
+    if (POL) { pol_stream = make_l2_policy(2); pol_keep = make_l2_policy(1); }
 #pragma unroll
     for (int p = 0; p < PER; ++p) {
       const int t = tid + p * kThreads;
       c[p] = 0;
       v[p] = 1.0;
       if (t < nn) {
-        c[p] = ld_stream_s32(cols + j0 + t);
-        if (VALS) v[p] = ld_stream_f64(vals + j0 + t);
+        c[p] = POL ? ld_stream_s32_pol(cols + j0 + t, pol_stream) : ld_stream_s32(cols + j0 + t);
+        if (VALS) v[p] = POL ? ld_stream_f64_pol(vals + j0 + t, pol_stream) : ld_stream_f64(vals + j0 + t);
       }
     }
 #pragma unroll
     for (int p = 0; p < PER; ++p) {
       const int t = tid + p * kThreads;
 #pragma unroll
-      for (int k = 0; k < RT; ++k) xv[p][k] = (t < nn) ? __ldg(X + (long long)c[p] * RT + k) : 0.0;
+      for (int k = 0; k < RT; ++k) {
+        xv[p][k] = 0.0;
+        if (t < nn) {
+          if (POL) XLoad<1>::ldp(&xv[p][k], X + (long long)c[p] * RT + k, pol_keep);
+          else xv[p][k] = __ldg(X + (long long)c[p] * RT + k);
+        }
+      }
     }
 #pragma unroll
     for (int p = 0; p < PER; ++p) {
@@ -202,10 +213,14 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
     FSB_KERNEL_CHECK();
     A->split_tile = kTile;
   }
-  if ((double)A->ncol * RT * 8.0 <= 32e6)
-    csr_stream_kernel<RT, VALS, 6><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
-  else
-    csr_stream_kernel<RT, VALS, 4><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, carry_row, carry_val);
+  const bool small_x = (double)A->ncol * RT * 8.0 <= 32e6;
+  const bool pol = fsb_knob("stream_policy", 1) != 0;
+#define FSB_STREAM_LAUNCH(MINB_, POL_)                                                                               \
+  csr_stream_kernel<RT, VALS, MINB_, POL_><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, \
+                                                                        A->split, carry_row, carry_val)
+  if (small_x) { if (pol) FSB_STREAM_LAUNCH(6, true); else FSB_STREAM_LAUNCH(6, false); }
+  else         { if (pol) FSB_STREAM_LAUNCH(4, true); else FSB_STREAM_LAUNCH(4, false); }
+#undef FSB_STREAM_LAUNCH
   FSB_KERNEL_CHECK();
   csr_stream_fixup_kernel<RT><<<(ntiles + 255) / 256, 256, 0, st>>>(ntiles, carry_row, carry_val, dY);
   FSB_KERNEL_CHECK();
