@@ -41,8 +41,8 @@ static inline void cbcsr_from_sbm(struct ColBinaryCSR* A, struct SparseBinaryMat
 
 /* Y = A X with ncol right-hand sides (new: the reference has one RHS only) */
 static inline void cbcsr_A_mul_Bn(double* Y, struct ColBinaryCSR* A, double* X, int ncol) {
-  fsb_matrix_t h = fsb_cache_cbcsr(A->nrow, A->ncol, A->nblocks, A->colblocksize, A->nnz, A->row_ptr, A->cols);
-  if (!h || fsb_spmm_host(h, Y, X, ncol)) fsb_die("cbcsr_A_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("cbcsr_A_mul_Bn", (h = fsb_cache_cbcsr(A->nrow, A->ncol, A->nblocks, A->colblocksize, A->nnz, A->row_ptr, A->cols)) != NULL, fsb_spmm_host(h, Y, X, ncol));
 }
 
 /* y = A x (cbcsr.h:76-106) */

@@ -23,18 +23,22 @@ static inline void fsb_cg_check_pair_(struct BlockedSBM* A, struct BlockedSBM* A
 
 /* y = At (A x) + lambda x; tmp (A->nrow doubles) receives A x (cg.h:9-22) */
 static inline void bsbm_AtA(double* y, struct BlockedSBM* A, struct BlockedSBM* At, double* x, double* tmp, double lambda) {
-  fsb_matrix_t ha = fsb_cache_blocked(A->nrow, A->ncol, A->nblocks, A->start_row, A->nnz, A->rows, A->cols, NULL);
-  fsb_matrix_t ht = fsb_cache_blocked(At->nrow, At->ncol, At->nblocks, At->start_row, At->nnz, At->rows, At->cols, NULL);
-  if (!ha || !ht || fsb_ata_pair_host(ha, ht, y, x, 1, lambda, tmp)) fsb_die("bsbm_AtA");
+  fsb_matrix_t ha, ht;
+  FSB_DROPIN_CALL("bsbm_AtA",
+                  (ha = fsb_cache_blocked(A->nrow, A->ncol, A->nblocks, A->start_row, A->nnz, A->rows, A->cols, NULL)) != NULL &&
+                  (ht = fsb_cache_blocked(At->nrow, At->ncol, At->nblocks, At->start_row, At->nnz, At->rows, At->cols, NULL)) != NULL,
+                  fsb_ata_pair_host(ha, ht, y, x, 1, lambda, tmp));
 }
 
 /* solves (A'A + lambda I) X = B for ncol <= 32 right-hand sides, X and B row-major [F][ncol] */
 static inline void bsbm_cgn(double* X, struct BlockedSBM* A, struct BlockedSBM* At, double* B, int ncol, double lambda,
                             double tol, int* out_iter) {
   fsb_cg_check_pair_(A, At);
-  fsb_matrix_t ha = fsb_cache_blocked(A->nrow, A->ncol, A->nblocks, A->start_row, A->nnz, A->rows, A->cols, NULL);
-  fsb_matrix_t ht = fsb_cache_blocked(At->nrow, At->ncol, At->nblocks, At->start_row, At->nnz, At->rows, At->cols, NULL);
-  if (!ha || !ht || fsb_cg_host(ha, ht, X, B, ncol, lambda, tol, 0, out_iter)) fsb_die("bsbm_cg");
+  fsb_matrix_t ha, ht;
+  FSB_DROPIN_CALL("bsbm_cg",
+                  (ha = fsb_cache_blocked(A->nrow, A->ncol, A->nblocks, A->start_row, A->nnz, A->rows, A->cols, NULL)) != NULL &&
+                  (ht = fsb_cache_blocked(At->nrow, At->ncol, At->nblocks, At->start_row, At->nnz, At->rows, At->cols, NULL)) != NULL,
+                  fsb_cg_host(ha, ht, X, B, ncol, lambda, tol, 0, out_iter));
 }
 
 /* one right-hand side (cg.h:25-82) */

@@ -82,8 +82,8 @@ static inline void deserialize_from_file(struct BinaryCSR* bcsr, const char* fil
 
 /* ---- products: Y[nrow][R] = A X[ncol][R], row-major ("row-ordered") operands ---- */
 static inline void bcsr_A_mul_Bn(double* Y, struct BinaryCSR* A, double* X, const int ncol) {   /* csr.h:257-280 */
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL);
-  if (!h || fsb_spmm_host(h, Y, X, ncol)) fsb_die("bcsr_A_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bcsr_A_mul_Bn", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL)) != NULL, fsb_spmm_host(h, Y, X, ncol));
 }
 static inline void bcsr_A_mul_B(double* y, struct BinaryCSR* A, double* x) { bcsr_A_mul_Bn(y, A, x, 1); }        /* csr.h:149-161 */
 static inline void bcsr_A_mul_B2(double* Y, struct BinaryCSR* A, double* X) { bcsr_A_mul_Bn(Y, A, X, 2); }       /* csr.h:164-181 */
@@ -98,23 +98,23 @@ static inline void bcsr_A_mul_B32n(double* Y, struct BinaryCSR* A, double* X, co
 /* Y[ncol_A][R] = A' X[nrow][R]: CSR-side transposed product (new; the reference builds a
  * second CSR of the transposed COO instead, bench_a_mul_b.c:273-274) */
 static inline void bcsr_At_mul_Bn(double* Y, struct BinaryCSR* A, double* X, const int ncol) {
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL);
-  if (!h || fsb_spmm_t_host(h, Y, X, ncol)) fsb_die("bcsr_At_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bcsr_At_mul_Bn", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL)) != NULL, fsb_spmm_t_host(h, Y, X, ncol));
 }
 static inline void bcsr_At_mul_B(double* y, struct BinaryCSR* A, double* x) { bcsr_At_mul_Bn(y, A, x, 1); }
 
 /* y = A'A x: deterministic two-pass form (csr.h:305-319) */
 static inline void bcsr_AA_mul_B(double* y, struct BinaryCSR* A, double* x) {
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL);
-  if (!h || fsb_ata_host(h, y, x, 1, 0.0, 0)) fsb_die("bcsr_AA_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bcsr_AA_mul_B", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL)) != NULL, fsb_ata_host(h, y, x, 1, 0.0, 0));
 }
 
 /* y = A'A x: fused gather + fp64 red.global.add scatter (csr.h:323-355).  ytmp, the
  * per-thread scratch of the CPU version, is accepted and ignored. */
 static inline void parallel_bcsr_AA_mul_B(double* y, struct BinaryCSR* A, double* x, double* ytmp) {
   (void)ytmp;
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL);
-  if (!h || fsb_ata_host(h, y, x, 1, 0.0, 1)) fsb_die("parallel_bcsr_AA_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("parallel_bcsr_AA_mul_B", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, NULL)) != NULL, fsb_ata_host(h, y, x, 1, 0.0, 1));
 }
 
 /*** Double CSR ***/
@@ -149,14 +149,14 @@ static inline void new_csr(struct CSR* A, long nnz, int nrow, int ncol, int* row
 }
 
 static inline void csr_A_mul_Bn(double* Y, struct CSR* A, double* X, const int ncol) {   /* csr.h:441-465 */
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, A->vals);
-  if (!h || fsb_spmm_host(h, Y, X, ncol)) fsb_die("csr_A_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("csr_A_mul_Bn", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, A->vals)) != NULL, fsb_spmm_host(h, Y, X, ncol));
 }
 static inline void csr_A_mul_B(double* y, struct CSR* A, double* x) { csr_A_mul_Bn(y, A, x, 1); }   /* csr.h:425-438 */
 
 static inline void csr_At_mul_Bn(double* Y, struct CSR* A, double* X, const int ncol) {   /* new, see bcsr_At_mul_Bn */
-  fsb_matrix_t h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, A->vals);
-  if (!h || fsb_spmm_t_host(h, Y, X, ncol)) fsb_die("csr_At_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("csr_At_mul_Bn", (h = fsb_cache_csr(A->nrow, A->ncol, A->nnz, A->row_ptr, A->cols, A->vals)) != NULL, fsb_spmm_t_host(h, Y, X, ncol));
 }
 static inline void csr_At_mul_B(double* y, struct CSR* A, double* x) { csr_At_mul_Bn(y, A, x, 1); }
 

@@ -47,14 +47,14 @@ static inline void sdm_transpose(struct SparseDoubleMatrix* A) {
 
 /* y = A x (replaces the serial loop dsparse.h:43-51) */
 static inline void sdm_A_mul_B(double* y, struct SparseDoubleMatrix* A, double* x) {
-  fsb_matrix_t h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals);
-  if (!h || fsb_spmm_host(h, y, x, 1)) fsb_die("sdm_A_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("sdm_A_mul_B", (h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals)) != NULL, fsb_spmm_host(h, y, x, 1));
 }
 
 /* y = A' x (replaces dsparse.h:54-62) */
 static inline void sdm_At_mul_B(double* y, struct SparseDoubleMatrix* A, double* x) {
-  fsb_matrix_t h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals);
-  if (!h || fsb_spmm_t_host(h, y, x, 1)) fsb_die("sdm_At_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("sdm_At_mul_B", (h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals)) != NULL, fsb_spmm_t_host(h, y, x, 1));
 }
 
 /* raw COO file with values (dsparse.h:64-93) */
@@ -117,14 +117,14 @@ static inline struct BlockedSDM* new_bsdm(struct SparseDoubleMatrix* A, int bloc
 
 /* y = B x (dsparse.h:176-191) */
 static inline void bsdm_A_mul_B(double* y, struct BlockedSDM* B, double* x) {
-  fsb_matrix_t h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, B->vals);
-  if (!h || fsb_spmm_host(h, y, x, 1)) fsb_die("bsdm_A_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bsdm_A_mul_B", (h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, B->vals)) != NULL, fsb_spmm_host(h, y, x, 1));
 }
 
 /* n right-hand sides on the double-valued blocked format (no reference counterpart) */
 static inline void bsdm_A_mul_Bn(double* y, struct BlockedSDM* B, double* x, int ncol) {
-  fsb_matrix_t h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, B->vals);
-  if (!h || fsb_spmm_host(h, y, x, ncol)) fsb_die("bsdm_A_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bsdm_A_mul_Bn", (h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, B->vals)) != NULL, fsb_spmm_host(h, y, x, ncol));
 }
 
 /* per-block Hilbert order carrying the values (dsparse.h:193-216) */

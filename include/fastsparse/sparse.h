@@ -70,14 +70,14 @@ static inline void transpose(struct SparseBinaryMatrix* A) {
 /* y = A x on the GPU (replaces the serial COO loop sparse.h:58-65).  The COO is turned
  * into CSR on the device by a stable sort, so each y[r] sums the same terms. */
 static inline void A_mul_B(double* y, struct SparseBinaryMatrix* A, double* x) {
-  fsb_matrix_t h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL);
-  if (!h || fsb_spmm_host(h, y, x, 1)) fsb_die("A_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("A_mul_B", (h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL)) != NULL, fsb_spmm_host(h, y, x, 1));
 }
 
 /* y = A' x on the GPU (replaces sparse.h:68-75) */
 static inline void At_mul_B(double* y, struct SparseBinaryMatrix* A, double* x) {
-  fsb_matrix_t h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL);
-  if (!h || fsb_spmm_t_host(h, y, x, 1)) fsb_die("At_mul_B");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("At_mul_B", (h = fsb_cache_coo(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL)) != NULL, fsb_spmm_t_host(h, y, x, 1));
 }
 
 /* exponential variates and the geometric-skip subsampler (sparse.h:77-110): host-side
@@ -167,8 +167,8 @@ static inline void sort_bsbm_byrow(struct BlockedSBM* B) {
 
 /* Y = B X with ncol right-hand sides, row-major operands (sparse.h:318-336) */
 static inline void bsbm_A_mul_Bn(double* y, struct BlockedSBM* B, double* x, int ncol) {
-  fsb_matrix_t h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, NULL);
-  if (!h || fsb_spmm_host(h, y, x, ncol)) fsb_die("bsbm_A_mul_Bn");
+  fsb_matrix_t h;
+  FSB_DROPIN_CALL("bsbm_A_mul_Bn", (h = fsb_cache_blocked(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, NULL)) != NULL, fsb_spmm_host(h, y, x, ncol));
 }
 static inline void bsbm_A_mul_B(double* y, struct BlockedSBM* B, double* x) { bsbm_A_mul_Bn(y, B, x, 1); }   /* sparse.h:259-273 */
 static inline void bsbm_A_mul_B2(double* y, struct BlockedSBM* B, double* x) { bsbm_A_mul_Bn(y, B, x, 2); }  /* sparse.h:276-293 */

@@ -54,6 +54,7 @@ enum fsb_format {
 /* ---------------------------------------------------------------- runtime */
 int fsb_version(void);
 const char* fsb_last_error(void);
+int fsb_last_error_code(void);           /* the FSB_E* code that came with fsb_last_error() (for entry points returning handles) */
 int fsb_device_count(void);              /* 0 when no GPU / no driver       */
 int fsb_init(int device);                /* bind this thread's context; idempotent */
 int fsb_sync(void);                      /* synchronise the library stream  */
@@ -265,9 +266,18 @@ int fsb_csr_load_coo_file(fsb_matrix_t* out, const char* path, int with_vals);
 int fsb_csr_load_bin_file(fsb_matrix_t* out, const char* path, void* struct_image);
 
 /* ------------------------------------------------- drop-in plumbing */
-/* Used by the drop-in headers in include/fastsparse/.  A handle is cached per host structure, keyed
- * by its array pointers; mutating entry points (sort_*, transpose, free_*)
- * call fsb_cache_drop.  FSB_CACHE=0 in the environment disables caching. */
+/* Used by the drop-in headers in include/fastsparse/.  A handle is cached per host structure, keyed by its array
+ * pointers, and VALIDATED BY CONTENT on every lookup: the reference reads the caller's arrays on every call, so an
+ * in-place edit (or a free + re-allocation at the same address) must never be answered with the old matrix.
+ *   default / FSB_CACHE=1 : exact -- a 64-bit hash of the full content of every array.  Small structures are
+ *        hashed inline; large ones are hashed by a worker thread while the product already runs on the cached
+ *        copy, and fsb_cache_settle() reports whether that copy was stale (the header then repeats the call);
+ *   FSB_CACHE=fast : 256 strided samples per array only (for callers that promise not to edit in place);
+ *   FSB_CACHE=0    : no caching, every call uploads; the handles are released by fsb_cache_settle().
+ * The protocol every drop-in call follows is FSB_DROPIN_CALL below: lookups, the product, fsb_cache_settle();
+ * repeat while it returns non-zero.  Handles returned by fsb_cache_* are valid until the calling thread's next
+ * fsb_cache_settle().  Mutating entry points (sort_*, transpose, free_*) also call fsb_cache_drop at once.
+ * Least-recently-used entries are evicted above FSB_CACHE_MAX_MB (default 65536) of HBM or 64 entries. */
 fsb_matrix_t fsb_cache_csr(int nrow, int ncol, long nnz, const int* row_ptr,
                            const int* cols, const double* vals);
 fsb_matrix_t fsb_cache_coo(int nrow, int ncol, long nnz, const int* rows,
@@ -279,6 +289,17 @@ fsb_matrix_t fsb_cache_blocked(int nrow, int ncol, int nblocks, const int* start
                                double* const* vals);
 void fsb_cache_drop(const void* key_ptr);
 void fsb_cache_clear(void);
+/* end of one drop-in call on this thread: number of handles that were stale copies (0 = the result stands) */
+int fsb_cache_settle(void);
+/* entries currently cached and the HBM bytes they hold (tests) */
+int fsb_cache_stats(long* entries, long* bytes);
+#define FSB_DROPIN_CALL(where, acquire_ok, run_rc)        \
+  do {                                                    \
+    for (;;) {                                            \
+      if (!(acquire_ok) || (run_rc)) fsb_die(where);      \
+      if (!fsb_cache_settle()) break;                     \
+    }                                                     \
+  } while (0)
 /* print fsb_last_error() and exit(1): the reference's error convention
  * (sparse.h:115-118, cg.h:32-36) */
 void fsb_die(const char* where);

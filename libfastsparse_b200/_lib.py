@@ -27,6 +27,7 @@ _LIB = None
 _SIGS = {
     "fsb_version": (C.c_int, []),
     "fsb_last_error": (C.c_char_p, []),
+    "fsb_last_error_code": (C.c_int, []),
     "fsb_device_count": (C.c_int, []),
     "fsb_init": (C.c_int, [C.c_int]),
     "fsb_sync": (C.c_int, []),
@@ -102,6 +103,8 @@ _SIGS = {
     "fsb_cache_blocked": (handle, [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp]),
     "fsb_cache_drop": (None, [C.c_void_p]),
     "fsb_cache_clear": (None, []),
+    "fsb_cache_settle": (C.c_int, []),
+    "fsb_cache_stats": (C.c_int, [c_long_p, c_long_p]),
     "fsb_die": (None, [C.c_char_p]),
     "fsb_tune_csr_spmm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "fsb_tune_csr_staged": (C.c_int, [C.c_int]),

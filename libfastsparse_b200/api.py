@@ -63,9 +63,17 @@ def launch_count() -> int:
 
 # ----------------------------------------------------------------------------- host structures
 class _Resident:
-    """Host structure with a lazily uploaded device twin."""
+    """Host structure with a device twin.
+
+    The drop-in-named functions below go through the library's residency cache exactly like the C headers
+    (fsb_cache_* + fsb_cache_settle): the host arrays stay the source of truth and are re-validated by content on every
+    call, so editing them in place between calls is safe.  `_dev()` is an explicit, privately owned snapshot used by
+    DeviceMatrix.of() for callers that keep a matrix resident and promise not to edit the host copy."""
 
     _h = None
+
+    def _cached(self):
+        raise NotImplementedError
 
     def _drop(self):
         if self._h:
@@ -96,6 +104,9 @@ class SparseBinaryMatrix(_Resident):      # sparse.h:11-18
             self._h = h
         return self._h
 
+    def _cached(self):
+        return lib().fsb_cache_coo(self.nrow, self.ncol, self.nnz, _ip(self.rows), _ip(self.cols), _dp(self.vals))
+
 
 class SparseDoubleMatrix(SparseBinaryMatrix):   # dsparse.h:11-19
     def __init__(self, nrow, ncol, rows, cols, vals):
@@ -120,6 +131,9 @@ class BinaryCSR(_Resident):               # csr.h:15-22
             self._h = h
         return self._h
 
+    def _cached(self):
+        return lib().fsb_cache_csr(self.nrow, self.ncol, self.nnz, _ip(self.row_ptr), _ip(self.cols), _dp(self.vals))
+
 
 class CSR(BinaryCSR):                     # csr.h:358-366
     pass
@@ -141,6 +155,9 @@ class ColBinaryCSR(_Resident):            # cbcsr.h:5-14
                                          _ip(self.row_ptr), _ip(self.cols)))
             self._h = h
         return self._h
+
+    def _cached(self):
+        return lib().fsb_cache_cbcsr(self.nrow, self.ncol, self.nblocks, self.colblocksize, self.nnz, _ip(self.row_ptr), _ip(self.cols))
 
 
 class BlockedSBM(_Resident):              # sparse.h:163-172
@@ -169,9 +186,28 @@ class BlockedSBM(_Resident):              # sparse.h:163-172
             self._h = h
         return self._h
 
+    def _cached(self):
+        # the pointer tables must outlive the call (the cache may hash the blocks on a worker thread until settle)
+        self._tables = (self._ptrs(self.rows, c_int_p), self._ptrs(self.cols, c_int_p),
+                        self._ptrs(self.vals, c_dbl_p) if self.vals is not None else None)
+        return lib().fsb_cache_blocked(self.nrow, self.ncol, self.nblocks, _ip(self.start_row), _ip(self.nnz), *self._tables)
+
 
 class BlockedSDM(BlockedSBM):             # dsparse.h:119-129
     pass
+
+
+def _dropin(structs, run):
+    """The drop-in call protocol of include/fastsparse/*.h (FSB_DROPIN_CALL): take the handles from the residency cache,
+    run, settle; repeat when a handle turned out to be a stale copy of arrays that were edited in place."""
+    while True:
+        hs = [st._cached() for st in structs]
+        if any(not h for h in hs):
+            lib().fsb_cache_settle()
+            check(lib().fsb_last_error_code() or 1)
+        check(run(*hs))
+        if lib().fsb_cache_settle() == 0:
+            return
 
 
 # ----------------------------------------------------------------------------- hilbert.h / quickSort*.h
@@ -254,13 +290,15 @@ def sort_sbm(A):                                              # sparse.h:142-161
 def A_mul_B(y, A, x):                                         # sparse.h:58-65 / dsparse.h:43-51
     x = _f64(x)
     assert x.size >= A.ncol
-    check(lib().fsb_spmm_host(A._dev(), _dp(_out(y, A.nrow)), _dp(x), 1))
+    yo = _out(y, A.nrow)
+    _dropin([A], lambda h: lib().fsb_spmm_host(h, _dp(yo), _dp(x), 1))
 
 
 def At_mul_B(y, A, x):                                        # sparse.h:68-75 / dsparse.h:54-62
     x = _f64(x)
     assert x.size >= A.nrow
-    check(lib().fsb_spmm_t_host(A._dev(), _dp(_out(y, A.ncol)), _dp(x), 1))
+    yo = _out(y, A.ncol)
+    _dropin([A], lambda h: lib().fsb_spmm_t_host(h, _dp(yo), _dp(x), 1))
 
 
 def _new_blocked(A, block_size, cls):
@@ -298,7 +336,8 @@ def sort_bsbm_byrow(B):                                       # sparse.h:238-256
 def bsbm_A_mul_Bn(y, B, x, ncol):                             # sparse.h:318-336
     x = _f64(x)
     assert x.size >= B.ncol * ncol
-    check(lib().fsb_spmm_host(B._dev(), _dp(_out(y, B.nrow * ncol)), _dp(x), ncol))
+    yo = _out(y, B.nrow * ncol)
+    _dropin([B], lambda h: lib().fsb_spmm_host(h, _dp(yo), _dp(x), ncol))
 
 
 def bsbm_A_mul_B(y, B, x):                                    # sparse.h:259-273
@@ -394,7 +433,8 @@ def deserialize_from_file(filename):                          # csr.h:117-146
 def bcsr_A_mul_Bn(Y, A, X, ncol):                             # csr.h:257-280 / 441-465
     X = _f64(X)
     assert X.size >= A.ncol * ncol
-    check(lib().fsb_spmm_host(A._dev(), _dp(_out(Y, A.nrow * ncol)), _dp(X), ncol))
+    Yo = _out(Y, A.nrow * ncol)
+    _dropin([A], lambda h: lib().fsb_spmm_host(h, _dp(Yo), _dp(X), ncol))
 
 
 def bcsr_A_mul_B32n(Y, A, X, ncol):                           # csr.h:283-302
@@ -425,13 +465,15 @@ def bcsr_At_mul_Bn(Y, A, X, ncol):
     """Y[ncol_A][ncol] = A' X -- CSR-side transposed product the reference lacks (SURVEY 8b "New")."""
     X = _f64(X)
     assert X.size >= A.nrow * ncol
-    check(lib().fsb_spmm_t_host(A._dev(), _dp(_out(Y, A.ncol * ncol)), _dp(X), ncol))
+    Yo = _out(Y, A.ncol * ncol)
+    _dropin([A], lambda h: lib().fsb_spmm_t_host(h, _dp(Yo), _dp(X), ncol))
 
 
 def bcsr_AA_mul_B(y, A, x, mode=0):                           # csr.h:305-319
     x = _f64(x)
     assert x.size >= A.ncol
-    check(lib().fsb_ata_host(A._dev(), _dp(_out(y, A.ncol)), _dp(x), 1, 0.0, mode))
+    yo = _out(y, A.ncol)
+    _dropin([A], lambda h: lib().fsb_ata_host(h, _dp(yo), _dp(x), 1, 0.0, mode))
 
 
 def parallel_bcsr_AA_mul_B(y, A, x, ytmp=None):               # csr.h:323-355 (ytmp: unused scratch of the CPU version)
@@ -461,7 +503,8 @@ def cbcsr_A_mul_Bn(Y, A, X, ncol):
     """n-RHS product on the column-blocked format (the reference has R = 1 only)."""
     X = _f64(X)
     assert X.size >= A.ncol * ncol
-    check(lib().fsb_spmm_host(A._dev(), _dp(_out(Y, A.nrow * ncol)), _dp(X), ncol))
+    Yo = _out(Y, A.nrow * ncol)
+    _dropin([A], lambda h: lib().fsb_spmm_host(h, _dp(Yo), _dp(X), ncol))
 
 
 def cbcsr_A_mul_B(y, A, x):                                   # cbcsr.h:76-106
@@ -526,8 +569,9 @@ def bsbm_AtA(y, A, At, x, tmp, lam):                          # cg.h:9-22
     _check_pair(A, At)
     x = _f64(x)
     assert x.size >= A.ncol
-    check(lib().fsb_ata_pair_host(A._dev(), At._dev(), _dp(_out(y, A.ncol)), _dp(x), 1, float(lam),
-                                  _dp(_out(tmp, A.nrow)) if tmp is not None else None))
+    yo = _out(y, A.ncol)
+    to = _out(tmp, A.nrow) if tmp is not None else None
+    _dropin([A, At], lambda ha, ht: lib().fsb_ata_pair_host(ha, ht, _dp(yo), _dp(x), 1, float(lam), _dp(to) if to is not None else None))
 
 
 def bsbm_cgn(X, A, At, B, ncol, lam, tol, max_iter=0):
@@ -537,7 +581,8 @@ def bsbm_cgn(X, A, At, B, ncol, lam, tol, max_iter=0):
     B = _f64(B)
     assert B.size >= A.ncol * ncol
     it = C.c_int(0)
-    check(lib().fsb_cg_host(A._dev(), At._dev(), _dp(_out(X, A.ncol * ncol)), _dp(B), ncol, float(lam), float(tol), int(max_iter), C.byref(it)))
+    Xo = _out(X, A.ncol * ncol)
+    _dropin([A, At], lambda ha, ht: lib().fsb_cg_host(ha, ht, _dp(Xo), _dp(B), ncol, float(lam), float(tol), int(max_iter), C.byref(it)))
     return it.value
 
 

@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", HOST_CXX, "-Xcompiler"
               "--expt-relaxed-constexpr", "-I", INCLUDE]
 
 SOURCES = ["fsb_capi.cu", "kernels_csr.cu", "kernels_csr_staged.cu", "kernels_csr_stream.cu", "kernels_cbcsr.cu", "kernels_blocked.cu", "kernels_build.cu",
-           "kernels_dense.cu", "fsb_cg.cu", "fsb_comm.cu", "fsb_io.cu", "fsb_host.cpp", "fsb_dropin.cpp"]
+           "kernels_dense.cu", "fsb_cg.cu", "fsb_comm.cu", "fsb_io.cu", "fsb_hostcopy.cu", "fsb_host.cpp", "fsb_dropin.cpp"]
 
 
 def _deps_mtime() -> float:

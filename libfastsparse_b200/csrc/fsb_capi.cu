@@ -16,6 +16,7 @@
 
 namespace {
 thread_local char tl_error[512] = "";
+thread_local int tl_error_code = 0;
 std::mutex g_init_mu;
 bool g_inited = false;
 int g_device = -1;
@@ -30,6 +31,7 @@ int fsb_set_error(int code, const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(tl_error, sizeof tl_error, fmt, ap);
   va_end(ap);
+  tl_error_code = code;
   return code;
 }
 
@@ -84,6 +86,7 @@ extern "C" {
 
 int fsb_version(void) { return 100; }
 const char* fsb_last_error(void) { return tl_error; }
+int fsb_last_error_code(void) { return tl_error_code; }
 long fsb_launch_count(void) { return g_launches.load(); }
 
 int fsb_device_count(void) {
@@ -157,6 +160,7 @@ static void free_arrays(fsb_matrix* A) {
   if (A->cg_cache && A->cg_cache_free) A->cg_cache_free(A->cg_cache);
   A->cg_cache = nullptr;
   cudaFree(A->carry);
+  cudaFree(A->xpack);
   cudaFree(A->split);
   cudaFree(A->row_ptr); cudaFree(A->cols); cudaFree(A->vals);
   cudaFree(A->start_row); cudaFree(A->blk_off); cudaFree(A->b_rows); cudaFree(A->b_cols); cudaFree(A->b_vals);
@@ -168,7 +172,7 @@ static void free_arrays(fsb_matrix* A) {
 template <typename T>
 static int upload_array(T** dst, const T* src, size_t n, cudaStream_t st) {
   FSB_CUDA(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
-  if (n) FSB_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+  if (n) FSB_TRY(fsb_h2d(*dst, src, n * sizeof(T), st));   // pageable sources go through the pinned bounce ring
   return FSB_OK;
 }
 
@@ -522,10 +526,11 @@ int fsb_noise_rhs_dev(fsb_matrix_t A, fsb_matrix_t At, double* dB, int R, double
 // produced in row chunks so the D2H copy of chunk i overlaps the kernel of chunk i+1.
 namespace {
 
+constexpr int kHostChunks = 8;
 struct HostStage {
   double* dX = nullptr; size_t capX = 0;
   double* dY = nullptr; size_t capY = 0;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev[kHostChunks] = {};
 };
 HostStage g_stage;
 std::mutex g_stage_mu;
@@ -539,10 +544,8 @@ int stage_reserve(size_t bx, size_t by) {
     cudaFree(g_stage.dY); g_stage.dY = nullptr; g_stage.capY = 0;
     FSB_CUDA(cudaMalloc(&g_stage.dY, by)); g_stage.capY = by;
   }
-  if (!g_stage.ev[0]) {
-    FSB_CUDA(cudaEventCreateWithFlags(&g_stage.ev[0], cudaEventDisableTiming));
-    FSB_CUDA(cudaEventCreateWithFlags(&g_stage.ev[1], cudaEventDisableTiming));
-  }
+  if (!g_stage.ev[0])
+    for (auto& e : g_stage.ev) FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return FSB_OK;
 }
 
@@ -555,8 +558,19 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
   if (!A || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_spmm_host: bad argument");
   std::lock_guard<std::mutex> lk(g_stage_mu);
   const size_t bx = (size_t)A->ncol * R * 8, by = (size_t)A->nrow * R * 8;
-  FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
-  if (bx) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, bx, cudaMemcpyHostToDevice, g_stream));
+  if (A->sharded && fsb_comm_active() && bx >= ((size_t)1 << 20)) {
+    // row shard of a multi-GPU product: X is the same on every rank's host, so each rank sends only its 1/G of it over
+    // PCIe and the rest arrives over NVLink (in-place all-gather) -- per-rank H2D drops from |X| to |X| / G
+    const int G = fsb_comm_size(), rk = fsb_comm_rank();
+    const size_t n = (size_t)A->ncol * R, per = (n + G - 1) / G;
+    FSB_TRY(stage_reserve(per * G * 8, std::max<size_t>(by, 8)));
+    const size_t lo = std::min(n, (size_t)rk * per), hi = std::min(n, lo + per);
+    FSB_TRY(fsb_h2d(g_stage.dX + lo, X + lo, (hi - lo) * 8, g_stream));
+    FSB_TRY(fsb_comm_allgather(g_stage.dX + (size_t)rk * per, g_stage.dX, per, g_stream));
+  } else {
+    FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
+    FSB_TRY(fsb_h2d(g_stage.dX, X, bx, g_stream));
+  }
   // Large results are dominated by the D2H copy of Y over PCIe.  Row chunks are independent, so
   // the product is issued chunk by chunk and chunk i is copied out (second stream) while chunk
   // i+1 is computed: the kernel time disappears behind the copy.
@@ -565,9 +579,11 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
     FSB_TRY(fsb_build_csr_view(A, g_stream));
     C = A->view;
   }
-  const int kChunks = 8;
+  const int kChunks = kHostChunks;
   if (C->format == FSB_FMT_CSR && R >= 2 && by >= ((size_t)64 << 20) && C->nrow >= 1024 * kChunks) {
     const int per = (C->nrow + kChunks - 1) / kChunks;
+    void* seg_dst[kHostChunks]; const void* seg_src[kHostChunks]; size_t seg_bytes[kHostChunks];
+    int nseg = 0;
     for (int c = 0; c < kChunks; ++c) {
       const int r0 = c * per, r1 = std::min(C->nrow, r0 + per);
       if (r0 >= r1) break;
@@ -578,16 +594,19 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
       double* dYc = g_stage.dY + (size_t)r0 * R;
       FSB_TRY(fsb_launch_csr_spmm(&part, dYc, g_stage.dX, R, g_stream));
       fsb_copy_tuning(C, &part);
-      FSB_CUDA(cudaEventRecord(g_stage.ev[c & 1], g_stream));
-      FSB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_stage.ev[c & 1], 0));
-      FSB_CUDA(cudaMemcpyAsync(Y + (size_t)r0 * R, dYc, (size_t)(r1 - r0) * R * 8, cudaMemcpyDeviceToHost, g_copy_stream));
+      FSB_CUDA(cudaEventRecord(g_stage.ev[c], g_stream));
+      seg_dst[nseg] = Y + (size_t)r0 * R; seg_src[nseg] = dYc; seg_bytes[nseg] = (size_t)(r1 - r0) * R * 8;
+      ++nseg;
     }
+    // every chunk's kernels are queued; the copy stream takes chunk c as soon as its event fires (pinned Y: direct
+    // DMA; malloc'd Y: through the pinned bounce ring with the host-side copies overlapped, fsb_hostcopy.cu)
+    FSB_TRY(fsb_d2h_segments(nseg, seg_dst, seg_src, seg_bytes, g_stage.ev, g_copy_stream));
     FSB_CUDA(cudaStreamSynchronize(g_copy_stream));
     FSB_CUDA(cudaStreamSynchronize(g_stream));
     return FSB_OK;
   }
   FSB_TRY(spmm_any(A, g_stage.dY, g_stage.dX, R, g_stream));
-  if (by) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, by, cudaMemcpyDeviceToHost, g_stream));
+  FSB_TRY(fsb_d2h(Y, g_stage.dY, by, g_stream));
   FSB_CUDA(cudaStreamSynchronize(g_stream));
   return FSB_OK;
 }
@@ -598,9 +617,9 @@ int fsb_spmm_t_host(fsb_matrix_t A, double* Y, const double* X, int R) {
   std::lock_guard<std::mutex> lk(g_stage_mu);
   const size_t bx = (size_t)A->nrow * R * 8, by = (size_t)A->ncol * R * 8;
   FSB_TRY(stage_reserve(std::max<size_t>(bx, 8), std::max<size_t>(by, 8)));
-  if (bx) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, bx, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_h2d(g_stage.dX, X, bx, g_stream));
   FSB_TRY(fsb_spmm_t_dev(A, g_stage.dY, g_stage.dX, R, g_stream));
-  if (by) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, by, cudaMemcpyDeviceToHost, g_stream));
+  FSB_TRY(fsb_d2h(Y, g_stage.dY, by, g_stream));
   FSB_CUDA(cudaStreamSynchronize(g_stream));
   return FSB_OK;
 }
@@ -611,9 +630,9 @@ int fsb_ata_host(fsb_matrix_t A, double* Y, const double* X, int R, double lambd
   std::lock_guard<std::mutex> lk(g_stage_mu);
   const size_t b = (size_t)A->ncol * R * 8;
   FSB_TRY(stage_reserve(std::max<size_t>(b, 8), std::max<size_t>(b, 8)));
-  if (b) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, b, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_h2d(g_stage.dX, X, b, g_stream));
   FSB_TRY(fsb_ata_dev(A, g_stage.dY, g_stage.dX, R, lambda, nullptr, mode, g_stream));
-  if (b) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, b, cudaMemcpyDeviceToHost, g_stream));
+  FSB_TRY(fsb_d2h(Y, g_stage.dY, b, g_stream));
   FSB_CUDA(cudaStreamSynchronize(g_stream));
   return FSB_OK;
 }
@@ -626,10 +645,10 @@ int fsb_ata_pair_host(fsb_matrix_t A, fsb_matrix_t At, double* Y, const double* 
   FSB_TRY(stage_reserve(std::max<size_t>(b, 8), std::max<size_t>(b, 8)));
   double* dTmp = nullptr;
   FSB_TRY(fsb_matrix_scratch(A, std::max<size_t>(bt, 8), &dTmp));
-  if (b) FSB_CUDA(cudaMemcpyAsync(g_stage.dX, X, b, cudaMemcpyHostToDevice, g_stream));
+  FSB_TRY(fsb_h2d(g_stage.dX, X, b, g_stream));
   FSB_TRY(fsb_ata_pair_dev(A, At, g_stage.dY, g_stage.dX, R, lambda, dTmp, g_stream));
-  if (b) FSB_CUDA(cudaMemcpyAsync(Y, g_stage.dY, b, cudaMemcpyDeviceToHost, g_stream));
-  if (tmp && bt) FSB_CUDA(cudaMemcpyAsync(tmp, dTmp, bt, cudaMemcpyDeviceToHost, g_stream));
+  FSB_TRY(fsb_d2h(Y, g_stage.dY, b, g_stream));
+  if (tmp) FSB_TRY(fsb_d2h(tmp, dTmp, bt, g_stream));
   FSB_CUDA(cudaStreamSynchronize(g_stream));
   return FSB_OK;
 }

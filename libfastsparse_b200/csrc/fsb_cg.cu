@@ -518,14 +518,11 @@ extern "C" int fsb_cg_host(fsb_matrix_t A, fsb_matrix_t At, double* X, const dou
   cudaError_t e = cudaMalloc(&dB, bytes);
   cudaStream_t st = fsb_default_stream();
   int rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
-  if (rc == FSB_OK) {
-    e = cudaMemcpyAsync(dB, B, (size_t)A->ncol * R * 8, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) rc = fsb_cuda_error(e, "H2D", __FILE__, __LINE__);
-  }
+  if (rc == FSB_OK) rc = fsb_h2d(dB, B, (size_t)A->ncol * R * 8, st);
   if (rc == FSB_OK) rc = fsb_cg_dev(A, At, dX, dB, R, lambda, tol, max_iter, out_iter, (void*)st);
+  if (rc == FSB_OK) rc = fsb_d2h(X, dX, (size_t)A->ncol * R * 8, st);
   if (rc == FSB_OK) {
-    e = cudaMemcpyAsync(X, dX, (size_t)A->ncol * R * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fsb_cuda_error(e, "D2H", __FILE__, __LINE__);
   }
   cudaFree(dX); cudaFree(dB);

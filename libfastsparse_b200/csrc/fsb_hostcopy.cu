@@ -1,0 +1,160 @@
+// fsb_hostcopy.cu -- host <-> device copies for the host-pointer (drop-in) entry points.
+//
+// A C caller of the reference allocates every operand with malloc (bench_a_mul_b.c:125-139): PAGEABLE memory.
+// cudaMemcpyAsync from / to pageable memory degrades to the driver's synchronous staged copy (one thread, small
+// chunks: a fraction of the PCIe rate), and it cannot overlap anything.  Here pageable operands go through a
+// ring of pinned bounce buffers: the DMA engine moves bounce <-> HBM at wire speed while a few host threads move
+// bounce <-> the caller's array, so the two legs overlap and the host leg is not one core's memcpy rate.
+// Pinned or registered pointers (torch pinned tensors, cudaHostAlloc, cudaHostRegister) are detected with
+// cudaPointerGetAttributes and copied directly.  Nothing is ever registered behind the caller's back, so there is
+// no lifetime coupling with the caller's malloc / free.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+
+#include <omp.h>
+
+#include "fsb_internal.h"
+
+namespace {
+
+constexpr int kBuffers = 4;
+constexpr size_t kBounceBytes = (size_t)32 << 20;
+
+struct Ring {
+  char* buf[kBuffers] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kBuffers] = {nullptr, nullptr, nullptr, nullptr};
+  bool ready = false;
+};
+Ring g_ring;
+std::mutex g_ring_mu;   // one pageable transfer at a time (the ring is shared)
+
+int ring_init() {
+  if (g_ring.ready) return FSB_OK;
+  for (int i = 0; i < kBuffers; ++i) {
+    FSB_CUDA(cudaHostAlloc((void**)&g_ring.buf[i], kBounceBytes, cudaHostAllocDefault));
+    FSB_CUDA(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
+  }
+  g_ring.ready = true;
+  return FSB_OK;
+}
+
+int copy_threads() {
+  static int n = 0;
+  if (n == 0) {
+    const char* e = getenv("FSB_COPY_THREADS");
+    int want = e ? atoi(e) : 8;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0) want = std::min(want, hw);
+    n = std::max(want, 1);
+  }
+  return n;
+}
+
+// bounce <-> caller memory with a few threads (explicit num_threads: torchrun exports OMP_NUM_THREADS=1)
+void host_copy(void* dst, const void* src, size_t bytes) {
+  const int nt = copy_threads();
+  if (nt == 1 || bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
+  const size_t piece = (size_t)1 << 20;
+  const long np = (long)((bytes + piece - 1) / piece);
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (long p = 0; p < np; ++p) {
+    const size_t off = (size_t)p * piece;
+    memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
+  }
+}
+
+}  // namespace
+
+bool fsb_host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// dst (device) <- src (host).  Pinned source: one asynchronous copy on st.  Pageable source: pipelined through the
+// ring; returns when the source has been read completely (the device copies are still ordered on st).
+int fsb_h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return FSB_OK;
+  if (!fsb_host_is_pageable(src) || bytes < ((size_t)1 << 20)) {
+    FSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FSB_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  FSB_TRY(ring_init());
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += kBounceBytes, k = (k + 1) % kBuffers) {
+    const size_t n = std::min(kBounceBytes, bytes - off);
+    if (off >= kBuffers * kBounceBytes) FSB_CUDA(cudaEventSynchronize(g_ring.ev[k]));   // the copy that last used this buffer
+    host_copy(g_ring.buf[k], (const char*)src + off, n);
+    FSB_CUDA(cudaMemcpyAsync((char*)dst + off, g_ring.buf[k], n, cudaMemcpyHostToDevice, st));
+    FSB_CUDA(cudaEventRecord(g_ring.ev[k], st));
+  }
+  // the ring may be reused by the next transfer only when these copies have drained it
+  for (int i = 0; i < kBuffers; ++i) FSB_CUDA(cudaEventSynchronize(g_ring.ev[i]));
+  return FSB_OK;
+}
+
+// Copies `nseg` device segments to host memory in order.  Segment i may be read once ready[i] (an event recorded on
+// the producing stream; nullptr = already ordered on st) has fired.  Pinned destination: asynchronous copies on st,
+// returns immediately.  Pageable destination: pipelined through the ring, returns when every byte is in place.
+int fsb_d2h_segments(int nseg, void* const* dst, const void* const* src, const size_t* bytes, const cudaEvent_t* ready, cudaStream_t st) {
+  bool pageable = false;
+  for (int i = 0; i < nseg && !pageable; ++i) pageable = bytes[i] >= ((size_t)1 << 20) && fsb_host_is_pageable(dst[i]);
+  if (!pageable) {
+    for (int i = 0; i < nseg; ++i) {
+      if (!bytes[i]) continue;
+      if (ready && ready[i]) FSB_CUDA(cudaStreamWaitEvent(st, ready[i], 0));
+      FSB_CUDA(cudaMemcpyAsync(dst[i], src[i], bytes[i], cudaMemcpyDeviceToHost, st));
+    }
+    return FSB_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  FSB_TRY(ring_init());
+  // flatten into pieces of at most one bounce buffer
+  struct Piece { char* h; const char* d; size_t n; int seg; };
+  size_t total = 0;
+  for (int i = 0; i < nseg; ++i) total += (bytes[i] + kBounceBytes - 1) / kBounceBytes;
+  Piece* pc = (Piece*)malloc(std::max<size_t>(total, 1) * sizeof(Piece));
+  if (!pc) return fsb_set_error(FSB_ENOMEM, "fsb_d2h_segments: out of host memory");
+  size_t np = 0;
+  for (int i = 0; i < nseg; ++i)
+    for (size_t off = 0; off < bytes[i]; off += kBounceBytes) pc[np++] = Piece{(char*)dst[i] + off, (const char*)src[i] + off, std::min(kBounceBytes, bytes[i] - off), i};
+  int rc = FSB_OK;
+  int waited_seg = -1;
+  auto enqueue = [&](size_t p) -> cudaError_t {
+    const int k = (int)(p % kBuffers);
+    if (ready && pc[p].seg != waited_seg) {
+      waited_seg = pc[p].seg;
+      if (ready[waited_seg]) { cudaError_t e = cudaStreamWaitEvent(st, ready[waited_seg], 0); if (e != cudaSuccess) return e; }
+    }
+    cudaError_t e = cudaMemcpyAsync(g_ring.buf[k], pc[p].d, pc[p].n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(g_ring.ev[k], st);
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  for (size_t p = 0; p < np && p < (size_t)kBuffers && e == cudaSuccess; ++p) e = enqueue(p);
+  for (size_t p = 0; p < np && e == cudaSuccess; ++p) {
+    const int k = (int)(p % kBuffers);
+    e = cudaEventSynchronize(g_ring.ev[k]);
+    if (e != cudaSuccess) break;
+    host_copy(pc[p].h, g_ring.buf[k], pc[p].n);
+    if (p + kBuffers < np) e = enqueue(p + kBuffers);
+  }
+  if (e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_d2h_segments", __FILE__, __LINE__);
+  free(pc);
+  return rc;
+}
+
+int fsb_d2h(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  void* d[1] = {dst};
+  const void* s[1] = {src};
+  size_t b[1] = {bytes};
+  return fsb_d2h_segments(1, d, s, b, nullptr, st);
+}

@@ -35,6 +35,10 @@ struct fsb_matrix {
   // library-owned scratch (A X intermediate of A'A, host staging)
   double* tmp = nullptr;
   size_t tmp_cap = 0;
+  double* xpack = nullptr;    // dense operand repacked into contiguous column slabs [S][ncol][R/S] (fsb_launch_csr_spmm)
+  size_t xpack_cap = 0;
+  const double* xpack_src = nullptr;   // != nullptr: xpack already holds this operand (set around a chunked host product)
+  fsb_matrix* scratch_owner = nullptr; // row-range alias of another handle: scratch and tuning state live in the owner
   double* carry = nullptr;    // per-tile carries of the merge-path stream kernel
   size_t carry_cap = 0;
   int* split = nullptr;       // cached merge-path tile boundaries (rows complete at each tile start)
@@ -80,6 +84,13 @@ int fsb_knob(const char* name, int dflt);
 static inline cudaStream_t fsb_pick_stream(void* s) {
   return s ? (cudaStream_t)s : fsb_default_stream();
 }
+
+// ---- fsb_hostcopy.cu: host <-> device copies that stay at PCIe speed for pageable (malloc'd) host memory
+bool fsb_host_is_pageable(const void* p);
+int fsb_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+int fsb_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);
+int fsb_d2h_segments(int nseg, void* const* dst_host, const void* const* src_dev, const size_t* bytes, const cudaEvent_t* ready,
+                     cudaStream_t st);
 
 // ---- device scratch owned by a handle
 int fsb_matrix_scratch(fsb_matrix* A, size_t bytes, double** out);

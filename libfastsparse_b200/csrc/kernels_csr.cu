@@ -331,6 +331,43 @@ int run_config(fsb_matrix* A, double* dY, const double* dX, int R, int algo, int
   return FSB_OK;
 }
 
+// X [ncol][R] -> S contiguous column slabs [S][ncol][R/S]: one pass over the operand (2 x 8 ncol R bytes)
+__global__ void repack_slabs_kernel(const double2* __restrict__ X, double2* __restrict__ Xs, long long ncol, int R2, int w2) {
+  const long long n = ncol * R2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i / R2;
+    const int j = (int)(i - c * R2), s = j / w2, k = j - s * w2;
+    Xs[(long long)s * ncol * w2 + c * w2 + k] = X[i];
+  }
+}
+
+// The product as S column passes over CONTIGUOUS slabs of the dense operand.  A pass over columns [s w, (s+1) w) of
+// the row-major operand touches w*8 bytes out of every 8R-byte row: its L2 footprint is counted in 128-byte LINES,
+// so a 64-byte slab of a 256-byte row still occupies a full line (and the slab spans the whole 8 ncol R address
+// range).  Repacked, slab s is ncol*w*8 contiguous bytes: every line it occupies is fully used and a 64 MB slab
+// really is 64 MB of L2.  Costs one streaming pass over the operand per product.
+int run_repacked(fsb_matrix* A, double* dY, const double* dX, int R, int slabs, cudaStream_t st, const double* dZ, double lambda, bool deep) {
+  fsb_matrix* S = A->scratch_owner ? A->scratch_owner : A;
+  const int w = R / slabs;
+  const size_t need = (size_t)A->ncol * R * sizeof(double);
+  if (need > S->xpack_cap) {
+    if (S->xpack) cudaFree(S->xpack);
+    S->xpack = nullptr; S->xpack_cap = 0; S->xpack_src = nullptr;
+    FSB_CUDA(cudaMalloc(&S->xpack, need));
+    S->xpack_cap = need;
+  }
+  if (S->xpack_src != dX) {
+    const long long n = (long long)A->ncol * (R / 2);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    repack_slabs_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const double2*>(dX), reinterpret_cast<double2*>(S->xpack), A->ncol, R / 2, w / 2);
+    FSB_KERNEL_CHECK();
+  }
+  const int vec = 2, g = pow2_ceil(w / vec);
+  for (int s = 0; s < slabs; ++s)
+    FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, S->xpack + (size_t)s * A->ncol * w, R, s * w, w, g, vec, st, dZ, lambda, deep, w, 0));
+  return FSB_OK;
+}
+
 int stream_config(fsb_matrix* A, double* dY, const double* dX, int R, cudaStream_t st, const double* dZ, double lambda) {
   FSB_TRY(fsb_launch_csr_stream(A, dY, dX, R, st));
   if (dZ) FSB_TRY(fsb_dense_axpy_lambda(dY, dZ, lambda, (long)A->nrow * R, st));
@@ -373,6 +410,11 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   int vec = (R % 4 == 0 && al % 32 == 0 && (algo == 1 || R > 64)) ? 4 : (R % 2 == 0 && R >= 4 && al % 16 == 0) ? 2 : 1;
   if (g_vec && (R % g_vec == 0) && (al % (8 * g_vec) == 0)) vec = g_vec;
   int per_pass = std::min(R, 32 * vec);
+  {   // experiment knob: S contiguous (repacked) column slabs
+    const int xs = fsb_knob("x_slabs", 0);
+    if (algo == 2 && xs >= 2 && R % (2 * xs) == 0 && R <= 64 && al % 16 == 0)
+      return run_repacked(A, dY, dX, R, xs, st, dZ, lambda, g_deep > 0);
+  }
   if (g_slabs >= 1) {   // explicit choice (tools/sweep.py)
     if (g_slabs > 1 && per_pass % (g_slabs * vec) == 0) per_pass /= g_slabs;
     return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda, g_deep > 0);

@@ -111,8 +111,10 @@ def _cpu_has_avx512() -> bool:
 
 
 def _load_oracle():
-    if not os.path.exists(_ORACLE_SO):
-        build()
+    stale = not os.path.exists(_ORACLE_SO) or any(
+        os.path.getmtime(_ORACLE_SO) < os.path.getmtime(os.path.join(_HERE, f)) for f in ("fsoracle.c", "fsoracle.h"))
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "oracle"], check=True, capture_output=True)
     L = C.CDLL(_ORACLE_SO)
     L.fso_xy2d.restype = C.c_long
     L.fso_row_xy2d.restype = C.c_long
@@ -144,6 +146,8 @@ def _load_oracle():
     L.fso_blocked_AtA.argtypes = [c_dbl_p, C.POINTER(Blocked), C.POINTER(Blocked), c_dbl_p, c_dbl_p, C.c_double]
     L.fso_blocked_cg.argtypes = [c_dbl_p, C.POINTER(Blocked), C.POINTER(Blocked), c_dbl_p, C.c_double, C.c_double]
     L.fso_blocked_cg2.argtypes = [c_dbl_p, C.POINTER(Blocked), C.POINTER(Blocked), c_dbl_p, C.c_double, C.c_double]
+    L.fso_synth_coo.argtypes = [C.c_ulonglong, C.c_int, C.c_long, C.c_long, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p]
+    L.fso_synth_coo.restype = None
     L.fso_read_coo_file.argtypes = [C.c_char_p, c_long_p, c_long_p, c_long_p, c_int_p, c_int_p, c_dbl_p]
     L.fso_write_csr_bin.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_long, c_int_p, c_int_p]
     L.fso_read_csr_bin.argtypes = [C.c_char_p, c_int_p, c_int_p, c_long_p, c_int_p, c_int_p]
@@ -238,6 +242,15 @@ def blocked_from_coo(nrow, ncol, block_size, rows, cols, vals=None):
     O.fso_blocked_from_coo(rows.size, nrow, ncol, block_size, ip(rows), ip(cols),
                            dp(f64(vals)) if vals is not None else None, B.ref())
     return B
+
+
+def synth_coo(seed, dist, nnz, nrow, ncol, with_vals=False, j0=0):
+    """Entries [j0, j0+nnz) of the benchmark's counter-based COO stream (same bits as the product's generator)."""
+    rows = np.empty(max(nnz, 1), np.int32)
+    cols = np.empty(max(nnz, 1), np.int32)
+    vals = np.empty(max(nnz, 1), np.float64) if with_vals else None
+    O.fso_synth_coo(seed, dist, j0, nnz, nrow, ncol, ip(rows), ip(cols), dp(vals))
+    return rows[:nnz], cols[:nnz], (vals[:nnz] if with_vals else None)
 
 
 def csr_mul(nrow, row_ptr, cols, vals, X, R):

@@ -598,3 +598,44 @@ done:
   fclose(f);
   return rc;
 }
+
+/* ------------------------------------------------------------------ synthetic inputs
+ * The benchmark's input generator ("generated once on the host in C, shared by both paths"): splitmix64
+ * finaliser over (seed, 3j + k), scaled to the index range by the high word of a 64 x 32-bit product. */
+static uint64_t syn_mix(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static uint32_t syn_scale(uint64_t h, uint32_t n) {
+  const uint64_t hi = h >> 32, lo = h & 0xffffffffull;
+  return (uint32_t)((hi * n + ((lo * n) >> 32)) >> 32);
+}
+static uint64_t syn_gcd(uint64_t x, uint64_t y) { while (y) { uint64_t t = x % y; x = y; y = t; } return x; }
+
+void fso_synth_coo(unsigned long long seed, int dist, long j0, long n, int nrow, int ncol,
+                   int* rows, int* cols, double* vals) {
+  int nbits = 0;                                  /* octaves covering [1, ncol] */
+  while ((1ll << nbits) <= (long long)ncol) ++nbits;
+  uint64_t a = 2654435761ull % (uint64_t)(ncol > 0 ? ncol : 1);   /* affine column scatter, made coprime with ncol */
+  if (a == 0) a = 1;
+  while (ncol > 0 && syn_gcd(a, (uint64_t)ncol) != 1) ++a;
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) {
+    const uint64_t j = (uint64_t)(j0 + i);
+    if (rows) rows[i] = (int)syn_scale(syn_mix(seed ^ (3 * j)), (uint32_t)nrow);
+    if (cols) {
+      const uint64_t h = syn_mix(seed ^ (3 * j + 1));
+      if (dist == 0) {
+        cols[i] = (int)syn_scale(h, (uint32_t)ncol);
+      } else {
+        const uint32_t oct = syn_scale(h, (uint32_t)nbits);
+        uint64_t rank = (1ull << oct) + syn_scale(syn_mix(h), (uint32_t)(1u << oct));
+        rank = (rank - 1) % (uint64_t)ncol;
+        cols[i] = (int)((rank * a + 12345ull) % (uint64_t)ncol);
+      }
+    }
+    if (vals) vals[i] = (double)(syn_mix(seed ^ (3 * j + 2)) >> 11) * (1.0 / 9007199254740992.0);
+  }
+}

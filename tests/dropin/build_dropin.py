@@ -1,6 +1,7 @@
 """Builds the C callers of the drop-in headers (include/fastsparse/) into tests/_build/:
 
   dropin_test        tests/dropin/test_dropin.c -- our own C acceptance test (always)
+  time_dropin        tests/dropin/time_dropin.c -- bcsr_A_mul_Bn with malloc'd operands, timed (bench.py e2e.dropin_c)
   sampler_loop       examples/sampler_loop.c -- plain C against include/fsb.h alone (always)
   ref_test_sparse    the reference's test_sparse.c, UNMODIFIED, compiled from where it lies
   ref_bench_csr      ... bench_csr.c
@@ -42,6 +43,7 @@ def _cc(src, out, verbose, via_stdin=False, extra_inc=None):
 def build(verbose: bool = False):
     os.makedirs(OUT, exist_ok=True)
     built = [_cc(os.path.join(HERE, "test_dropin.c"), os.path.join(OUT, "dropin_test"), verbose),
+             _cc(os.path.join(HERE, "time_dropin.c"), os.path.join(OUT, "time_dropin"), verbose, extra_inc=os.path.join(ROOT, "include")),
              # plain C against the C ABI alone (include/fsb.h): the resident sampler loop
              _cc(os.path.join(ROOT, "examples", "sampler_loop.c"), os.path.join(OUT, "sampler_loop"), verbose, extra_inc=os.path.join(ROOT, "include"))]
     if os.path.isdir(REF):

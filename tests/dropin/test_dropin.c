@@ -173,6 +173,35 @@ int main(void) {
   pouter2(o3, xx, 2);
   CHECK(fabs(o3[2] - (0.12 * -0.82 + 1.3 * 0.5)) < 1e-12, "pouter2");
 
+  /* the host arrays stay the source of truth: an in-place edit between two calls must be seen (the reference reads
+   * vals[] on every call).  Large enough that the sampled fingerprint (256 strided samples) cannot see the edit and
+   * that the full-content hash runs on the background worker (> 4 MB of arrays). */
+  {
+    const int n = 600000, m = 64;
+    long nz = (long)n;
+    int* rr = malloc(nz * sizeof(int));
+    int* cc = malloc(nz * sizeof(int));
+    double* vv = malloc(nz * sizeof(double));
+    for (long j = 0; j < nz; j++) { rr[j] = (int)j; cc[j] = (int)(j % m); vv[j] = 1.0 + (j % 7); }
+    struct CSR Cs;
+    new_csr(&Cs, nz, n, m, rr, cc, vv);
+    double* xe = malloc(m * sizeof(double));
+    double* ye = malloc(n * sizeof(double));
+    for (int i = 0; i < m; i++) xe[i] = 1.0 + i;
+    csr_A_mul_B(ye, &Cs, xe);
+    const long k = 300001;                        /* not a multiple of nz/256: between two sampled positions */
+    const double before = ye[k];
+    Cs.vals[k] = 1000.0;
+    csr_A_mul_B(ye, &Cs, xe);
+    CHECK(fabs(before - (1.0 + (k % 7)) * xe[k % m]) < 1e-12, "product before the edit");
+    CHECK(fabs(ye[k] - 1000.0 * xe[k % m]) < 1e-9, "in-place edit of vals[] not seen: y=%g (stale device copy)", ye[k]);
+    Cs.cols[k] = (int)((k + 5) % m);
+    csr_A_mul_B(ye, &Cs, xe);
+    CHECK(fabs(ye[k] - 1000.0 * xe[(k + 5) % m]) < 1e-9, "in-place edit of cols[] not seen");
+    free_csr(&Cs);
+    free(rr); free(cc); free(vv); free(xe); free(ye);
+  }
+
   printf(failures ? "DROPIN TEST FAILED (%d)\n" : "DROPIN TEST PASSED\n", failures);
   return failures != 0;
 }

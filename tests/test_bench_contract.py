@@ -26,6 +26,38 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in line["config"] and "model" not in line["config"]
 
 
+def test_reference_arm_never_loads_the_product_library():
+    """The reference arm's inputs come from oracle/'s own generator: neither the python package nor the .so is loaded."""
+    code = ("import sys, bench; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'c2_small', '--steps', '1', '--warmup', '1', "
+            "'--sample-rows', '20000']; rc = bench.main(); maps = open('/proc/self/maps').read(); "
+            "assert rc == 0; assert 'libfastsparse_b200' not in sys.modules, 'package imported'; "
+            "assert 'libfastsparse_b200.so' not in maps, 'product .so mapped'; assert 'libfsoracle' in maps or 'libfsref' in maps")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_both_arms_print_the_same_config_object():
+    import bench
+    for n in (1, 2, 8):
+        c = bench.config_for("c2", n)
+        assert "workload" in c and "model" not in c and ("row-partitioned" in c["parallelism"]) == (n > 1)
+    # the reference arm's line carries exactly config_for(workload, gpus)
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--gpus", "2", "--workload", "c2_small", "--steps", "1", "--warmup", "1",
+                        "--sample-rows", "20000"], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["config"] == bench.config_for("c2_small", 2) and line["scaling"] == "strong"
+
+
+def test_reference_arm_default_is_the_whole_workload():
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--workload", "c2_small", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["detail"]["whole_workload"] is True and "the full c2_small matrix (1000000 rows, 20000000 nnz)" in line["cpu_baseline"]["sample"]
+
+
 def test_reference_arm_uses_all_host_threads_under_torchrun():
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must still use every usable core."""
     env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")

@@ -44,6 +44,43 @@ def test_dropin_c_acceptance():
     assert r.returncode == 0 and "DROPIN TEST PASSED" in r.stdout, r.stdout + r.stderr
 
 
+def _run_env(name, env, *args, timeout=300):
+    exe = os.path.join(BUILD, name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{name} not built")
+    return subprocess.run([exe, *args], cwd=GOLDEN, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **env))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["0", "fast", "1"])
+def test_dropin_c_acceptance_in_every_cache_mode(mode):
+    """FSB_CACHE=0 (no caching: two-matrix calls such as bsbm_cg / bsbm_AtA hold two transient handles until the
+    call settles -- round 1 freed the first one early), FSB_CACHE=fast, and the exact default."""
+    _ensure_built()
+    r = _run_env("dropin_test", {"FSB_CACHE": mode})
+    if mode == "fast":      # the sampled fingerprint cannot see the in-place edit: exactly that check fails, nothing else
+        assert "in-place edit" in r.stdout and r.stdout.count("FAIL") == 2, r.stdout + r.stderr
+    else:
+        assert r.returncode == 0 and "DROPIN TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_test_sparse_passes_without_the_cache():
+    r = _run_env("ref_test_sparse", {"FSB_CACHE": "0"})
+    assert r.returncode == 0 and "ALL TESTS PASSED" in r.stdout and "Tests run: 29" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_time_dropin_small():
+    """tests/dropin/time_dropin.c (bench.py's C-caller leg): malloc'd operands through bcsr_A_mul_Bn, self-checked."""
+    _ensure_built()
+    r = _run_env("time_dropin", {}, "200000", "30000", "4000000", "32", "2")
+    assert r.returncode == 0, r.stdout + r.stderr
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["max_abs_err_sampled_rows"] <= 1e-9 and line["ms_per_call"] > 0
+
+
 @pytest.mark.gpu
 def test_c_example_sampler_loop(tmp_path):
     """examples/sampler_loop.c: plain C on the C ABI alone -- file straight into HBM, device noise, block-CG solves."""

@@ -650,3 +650,54 @@ def test_device_cbcsr_builder_matches_host():
     Yh = fs.DeviceMatrix.of(Cb).spmm(X, R)
     D = fs.DeviceMatrix.cbcsr_from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), 256)
     assert D.nblocks == Cb.nblocks and torch.equal(D.spmm(X, R), Yh)
+
+
+# ------------------------------------------------------------------ residency cache (fsb_dropin.cpp)
+@pytest.mark.parametrize("n", [2000, 700000])        # inline full hash / background-worker hash (> 4 MB of arrays)
+def test_residency_cache_sees_in_place_edits(n):
+    """The host arrays are the source of truth (the reference reads them on every call): edits between two sampled
+    positions of the round-1 fingerprint, in vals[], cols[] and row_ptr[], must all be seen by the next product."""
+    m = 97
+    rows = np.arange(n, dtype=np.int32); cols = (np.arange(n) % m).astype(np.int32); vals = 1.0 + (np.arange(n) % 5)
+    M = fs.new_csr(n, n, m, rows, cols, vals)
+    x = 1.0 + np.arange(m, dtype=np.float64); y = np.zeros(n)
+    fs.csr_A_mul_B(y, M, x)
+    k = n // 2 + 1
+    assert y[k] == vals[k] * x[cols[k]]
+    M.vals[k] = 4096.0
+    fs.csr_A_mul_B(y, M, x)
+    assert y[k] == 4096.0 * x[cols[k]], "stale device copy after an in-place edit of vals[]"
+    M.cols[k] = (cols[k] + 3) % m
+    fs.csr_A_mul_B(y, M, x)
+    assert y[k] == 4096.0 * x[(cols[k] + 3) % m], "stale device copy after an in-place edit of cols[]"
+    # move one entry from row k to row k+1 (row_ptr edit)
+    M.row_ptr[k + 1] -= 1
+    fs.csr_A_mul_B(y, M, x)
+    assert y[k] == 0.0 and y[k + 1] == 4096.0 * x[(cols[k] + 3) % m] + vals[k + 1] * x[cols[k + 1]]
+    # unchanged arrays: served from the cache (no growth in entries)
+    e0 = C.c_long(); fs.lib().fsb_cache_stats(C.byref(e0), None)
+    fs.csr_A_mul_B(y, M, x)
+    e1 = C.c_long(); fs.lib().fsb_cache_stats(C.byref(e1), None)
+    assert e1.value == e0.value
+
+
+def test_residency_cache_evicts_least_recently_used(tmp_path):
+    """FSB_CACHE_MAX_MB caps the HBM the cache may pin: matrices whose host arrays were dropped with plain free()
+    (never fsb_cache_drop) do not accumulate."""
+    import subprocess, sys
+    code = r'''
+import ctypes as C, numpy as np, libfastsparse_b200 as fs
+keep = []
+for i in range(6):
+    n = 300000
+    M = fs.new_csr(n, n, 64, np.arange(n, dtype=np.int32), (np.arange(n) % 64).astype(np.int32), np.ones(n))
+    y = np.zeros(n); fs.csr_A_mul_B(y, M, np.ones(64)); assert y[5] == 1.0
+    keep.append(M)
+e, b = C.c_long(), C.c_long(); fs.lib().fsb_cache_stats(C.byref(e), C.byref(b))
+assert e.value <= 3 and b.value <= 12 << 20, (e.value, b.value)
+y = np.zeros(300000); fs.csr_A_mul_B(y, keep[0], np.ones(64)); assert y[7] == 1.0      # evicted entries are simply re-uploaded
+print("EVICT OK", e.value, b.value)
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FSB_CACHE_MAX_MB="12", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    assert r.returncode == 0 and "EVICT OK" in r.stdout, r.stdout + r.stderr

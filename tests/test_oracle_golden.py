@@ -263,3 +263,16 @@ def test_oracle_vs_live_reference(seed):
     Bref = BlockedMatrix(nrow, ncol, nnz, bs, False)
     REF.ref_new_bsbm(nnz, nrow, ncol, ip(rows), ip(cols), bs, Bref.ref()); REF.ref_sort_bsbm(Bref.ref())
     assert np.array_equal(B.rows, Bref.rows) and np.array_equal(B.cols, Bref.cols) and np.array_equal(B.blk_nnz, Bref.blk_nnz)
+
+
+def test_oracle_synth_generator_matches_the_product_generator_bit_for_bit():
+    """bench.py's reference arm draws its inputs from oracle/ (fso_synth_coo) so that it never loads the product
+    library; both generators must emit the identical COO stream, for both column distributions and any offset."""
+    import libfastsparse_b200 as fs
+    for dist, nrow, ncol in [(0, 100000, 7919), (1, 5000, 100003), (1, 77, 1), (0, 1, 1)]:
+        n = 200000
+        r1, c1, v1 = fs.synth_coo_host(0x5EED0002 + dist, dist, n, nrow, ncol, with_vals=True)
+        r2, c2, v2 = oracle.synth_coo(0x5EED0002 + dist, dist, n, nrow, ncol, with_vals=True)
+        assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
+        r3, c3, _ = oracle.synth_coo(0x5EED0002 + dist, dist, 1000, nrow, ncol, j0=12345)
+        assert np.array_equal(r3, r1[12345:13345]) and np.array_equal(c3, c1[12345:13345])

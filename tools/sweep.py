@@ -72,6 +72,8 @@ def main():
     for combo in combos:
         algo, tw, g, vec, slabs, rb = combo[:6]
         deep = combo[6] if len(combo) > 6 else -1
+        xslabs = combo[7] if len(combo) > 7 else 0      # optional 8th value: contiguous (repacked) column slabs of the dense operand
+        fs.check(fs.lib().fsb_tune(b"x_slabs", xslabs))
         fs.check(fs.lib().fsb_tune_csr_staged(deep))
         fs.check(fs.lib().fsb_tune_csr_algo(algo, rb, 0))
         fs.check(fs.lib().fsb_tune_csr_spmm(tw, g, vec, slabs))
@@ -93,7 +95,7 @@ def main():
         idx_bytes = 12 if args.vals else 4
         ab = nnz * (idx_bytes + 8 * R) + 4 * (nout + 1) + 8 * nout * R if 8 * nin * R > 126e6 else \
             nnz * idx_bytes + 4 * (nout + 1) + 8 * nout * R + 8 * nin * R
-        row = dict(algo=algo, tw=tw, g=g, vec=vec, slabs=slabs, rb=rb, deep=deep, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=ab / ms / 1e6, maxdiff=err)
+        row = dict(algo=algo, tw=tw, g=g, vec=vec, slabs=slabs, rb=rb, deep=deep, x_slabs=xslabs, ms=ms, nnz_rhs_per_s=nnz * R / ms * 1e3, alg_gbs=ab / ms / 1e6, maxdiff=err)
         rows.append(row)
         print(json.dumps(row), flush=True)
     if args.out:
