@@ -248,10 +248,17 @@ int fsb_blocked_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, const
   fsb_matrix* A = new fsb_matrix();
   A->format = FSB_FMT_BLOCKED; A->nrow = nrow; A->ncol = ncol; A->nblocks = nblocks; A->has_vals = vals != nullptr;
   std::vector<long> off((size_t)nblocks + 1, 0);
+  // start_row is host metadata (nblocks + 1 ints): validate it here.  It must run from 0 to nrow without decreasing,
+  // and (checked on the device below) every entry's row must lie inside its block -- the native kernel indexes the
+  // block's shared-memory Y slab with row - start_row[b].
+  bool meta_ok = nblocks == 0 ? true : (start_row[0] == 0 && start_row[nblocks] == nrow);
+  for (int b = 0; b < nblocks && meta_ok; ++b) meta_ok = start_row[b + 1] >= start_row[b] && blk_nnz[b] >= 0;
+  if (!meta_ok) { delete A; return fsb_set_error(FSB_EINVAL, "fsb_blocked_upload: start_row must run from 0 to nrow without decreasing (and block sizes be >= 0)"); }
   for (int b = 0; b < nblocks; ++b) {
     off[b + 1] = off[b] + blk_nnz[b];
     A->max_block_rows = std::max(A->max_block_rows, start_row[b + 1] - start_row[b]);
   }
+  if (off[nblocks] > (long)INT32_MAX) { delete A; return fsb_set_error(FSB_EINVAL, "fsb_blocked_upload: %ld entries do not fit int32 offsets", off[nblocks]); }
   A->nnz = off[nblocks];
   A->avg_row_nnz = nrow > 0 ? (double)A->nnz / nrow : 0.0;
   const size_t n1 = std::max<size_t>((size_t)A->nnz, 1);
@@ -271,6 +278,7 @@ int fsb_blocked_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, const
   }
   if (rc == FSB_OK) rc = fsb_check_index_range(A->b_rows, A->nnz, nrow, "row index", g_stream);
   if (rc == FSB_OK) rc = fsb_check_index_range(A->b_cols, A->nnz, ncol, "column index", g_stream);
+  if (rc == FSB_OK) rc = fsb_check_rows_in_blocks(A->b_rows, A->blk_off, A->start_row, nblocks, A->nnz, g_stream);
   if (rc == FSB_OK && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "upload sync", __FILE__, __LINE__);
   A->bytes = ((size_t)nblocks + 1) * 12 + n1 * (vals ? 16 : 8);
   if (rc == FSB_OK) rc = fsb_blocked_relayout(A, g_stream);
@@ -303,9 +311,11 @@ int fsb_matrix_tuning(fsb_matrix_t A, int transposed, int* R, int* passes, int* 
   if (!A) return fsb_set_error(FSB_EINVAL, "fsb_matrix_tuning: null handle");
   const fsb_matrix* M = A->format == FSB_FMT_CSR ? A : A->view;
   if (transposed) M = A->T;
-  if (R) *R = M ? M->tuned_R : 0;
-  if (passes) *passes = M ? M->tuned_passes : 1;
-  if (deep) *deep = M ? M->tuned_deep : 0;
+  const fsb_matrix::Tuned none;
+  const fsb_matrix::Tuned& t = (M && M->tuned_last >= 0) ? M->tuned[M->tuned_last] : none;
+  if (R) *R = t.R;
+  if (passes) *passes = t.passes;
+  if (deep) *deep = t.deep;
   return FSB_OK;
 }
 
@@ -588,12 +598,9 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
       const int r0 = c * per, r1 = std::min(C->nrow, r0 + per);
       if (r0 >= r1) break;
       fsb_matrix part;                 // rows [r0, r1): row_ptr values stay absolute, so cols/vals are shared
-      part.format = FSB_FMT_CSR; part.nrow = r1 - r0; part.ncol = C->ncol; part.nnz = C->nnz; part.has_vals = C->has_vals;
-      part.row_ptr = C->row_ptr + r0; part.cols = C->cols; part.vals = C->vals; part.avg_row_nnz = C->avg_row_nnz;
-      fsb_copy_tuning(&part, C);   // share the handle's autotune decision
+      fsb_make_row_alias(&part, C, r0, r1);
       double* dYc = g_stage.dY + (size_t)r0 * R;
       FSB_TRY(fsb_launch_csr_spmm(&part, dYc, g_stage.dX, R, g_stream));
-      fsb_copy_tuning(C, &part);
       FSB_CUDA(cudaEventRecord(g_stage.ev[c], g_stream));
       seg_dst[nseg] = Y + (size_t)r0 * R; seg_src[nseg] = dYc; seg_bytes[nseg] = (size_t)(r1 - r0) * R * 8;
       ++nseg;

@@ -278,11 +278,8 @@ int shard_apply_op(fsb_matrix* A, fsb_matrix* Acsr, fsb_matrix* T, CgShardWork& 
         FSB_TRY(fsb_launch_csr_spmm(T, w.KPpart, w.tmp, R, st));
       } else {
         fsb_matrix part;     // rows [r0, r1) of A_g': row_ptr values stay absolute, so cols / vals are shared
-        part.format = FSB_FMT_CSR; part.nrow = (int)(r1 - r0); part.ncol = T->ncol; part.nnz = T->nnz; part.has_vals = T->has_vals;
-        part.row_ptr = T->row_ptr + r0; part.cols = T->cols; part.vals = T->vals; part.avg_row_nnz = T->avg_row_nnz;
-        fsb_copy_tuning(&part, T);
+        fsb_make_row_alias(&part, T, (int)r0, (int)r1);
         FSB_TRY(fsb_launch_csr_spmm(&part, w.KPpart + (size_t)r0 * R, w.tmp, R, st));
-        fsb_copy_tuning(T, &part);
       }
     }
     FSB_CUDA(cudaEventRecord(w.ev[c], st));

@@ -44,9 +44,12 @@ struct fsb_matrix {
   int* split = nullptr;       // cached merge-path tile boundaries (rows complete at each tile start)
   int split_tile = 0;
   int max_row_nnz = -1;       // longest row (lazy; SpMV kernel choice)
-  int tuned_R = 0;            // autotune of the staged SpMM (see fsb_launch_csr_spmm): valid for this R,
-  int tuned_passes = 1;       //   column passes over the dense operand (1 or 2)
-  int tuned_deep = 0;         //   lean (0) or deep (1) build of the kernel
+  // autotune of the staged SpMM (see fsb_launch_csr_spmm), one slot per operand width R that has been timed on
+  // this handle (a CG solve alternates R = 32 products with R = 1 ones: no re-tuning when R changes back):
+  struct Tuned { int R = 0, passes = 1, deep = 0; };
+  Tuned tuned[6];             //   passes = column passes over the dense operand (1 or 2), deep = kernel build
+  int tuned_next = 0;         //   ring cursor
+  int tuned_last = -1;        //   slot used by the latest product (fsb_matrix_tuning reports it)
   size_t bytes = 0;
   double avg_row_nnz = 0.0;
   // solver workspace kept between solves on this handle (fsb_cg.cu); released with the handle
@@ -117,9 +120,27 @@ int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX
 // the event that says its half has arrived (the all-gather of the sharded CG, fsb_cg.cu).  R even, R/2 * 8 >= 128.
 int fsb_launch_csr_spmm_halves(fsb_matrix* A, double* dY, const double* dXlo, const double* dXhi, int R, cudaStream_t st,
                                cudaEvent_t ready_lo, cudaEvent_t ready_hi);
-// a row-range alias of a CSR handle (row_ptr offset, shared cols / vals) inherits and returns the autotune state
-inline void fsb_copy_tuning(fsb_matrix* dst, const fsb_matrix* src) {
-  dst->tuned_R = src->tuned_R; dst->tuned_passes = src->tuned_passes; dst->tuned_deep = src->tuned_deep;
+// A row-range ALIAS of a CSR handle (row_ptr + r0 with absolute offsets, shared cols / vals; lives on the caller's
+// stack) sets scratch_owner: scratch buffers and the autotune table live in the owner, and the dispatcher keeps
+// aliases on the row-local staged kernel (the merge-path kernel needs row_ptr[0] == 0 and per-handle tile tables).
+inline fsb_matrix* fsb_home(fsb_matrix* A) { return A->scratch_owner ? A->scratch_owner : A; }
+inline fsb_matrix::Tuned* fsb_tuned_find(fsb_matrix* A, int R) {
+  fsb_matrix* Hm = fsb_home(A);
+  for (int i = 0; i < 6; ++i)
+    if (Hm->tuned[i].R == R) { Hm->tuned_last = i; return &Hm->tuned[i]; }
+  return nullptr;
+}
+inline void fsb_tuned_store(fsb_matrix* A, int R, int passes, int deep) {
+  fsb_matrix* Hm = fsb_home(A);
+  const int i = Hm->tuned_next;
+  Hm->tuned[i].R = R; Hm->tuned[i].passes = passes; Hm->tuned[i].deep = deep;
+  Hm->tuned_last = i;
+  Hm->tuned_next = (i + 1) % 6;
+}
+inline void fsb_make_row_alias(fsb_matrix* part, fsb_matrix* C, int r0, int r1) {
+  part->format = FSB_FMT_CSR; part->nrow = r1 - r0; part->ncol = C->ncol; part->nnz = C->nnz; part->has_vals = C->has_vals;
+  part->row_ptr = C->row_ptr + r0; part->cols = C->cols; part->vals = C->vals; part->avg_row_nnz = C->avg_row_nnz;
+  part->scratch_owner = fsb_home(C);
 }
 void fsb_csr_staged_set_tuning(int rows_per_cta, int cap_mult);
 
@@ -131,6 +152,8 @@ int fsb_launch_blocked_spmm(const fsb_matrix* A, double* dY, const double* dX, i
 // input validation on the device (an out-of-range index would be an illegal address in the products)
 int fsb_check_index_range(const int* d_idx, long n, int limit, const char* what, cudaStream_t st);
 int fsb_check_row_ptr(const int* d_ptr, long n, long last, const char* what, cudaStream_t st);
+// every entry i of a blocked COO (block b = the one with blk_off[b] <= i < blk_off[b+1]) has start_row[b] <= rows[i] < start_row[b+1]?
+int fsb_check_rows_in_blocks(const int* d_rows, const long* d_blk_off, const int* d_start_row, int nblocks, long nnz, cudaStream_t st);
 int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
                                const int* d_cols, const double* d_vals, cudaStream_t st);
 int fsb_build_transpose(fsb_matrix* A, cudaStream_t st);   // fills A->T

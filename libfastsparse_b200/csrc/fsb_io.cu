@@ -81,6 +81,8 @@ int fsb_csr_load_coo_file(fsb_matrix_t* out, const char* path, int with_vals) {
   if (hdr[0] < 0 || hdr[1] < 0 || hdr[2] < 0 || hdr[0] > INT32_MAX || hdr[1] > INT32_MAX)
     return fsb_set_error(FSB_EIO, "File error: %s: bad header (%ld x %ld, %ld entries)", path, (long)hdr[0], (long)hdr[1], (long)hdr[2]);
   const long nnz = (long)hdr[2];
+  if (nnz > (long)INT32_MAX)   // before any allocation: the CSR offsets are int32 (csr.h:20)
+    return fsb_set_error(FSB_EINVAL, "%s: %ld entries do not fit the int32 offsets of the CSR structure", path, nnz);
   cudaStream_t st = fsb_default_stream();
   Pipe p;
   FSB_TRY(p.init());

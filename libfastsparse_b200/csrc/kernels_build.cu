@@ -149,6 +149,9 @@ int fsb_check_row_ptr(const int* d_ptr, long n, long last, const char* what, cud
 // Sort (key, payload...) stably by key in [0, nkeys) and emit CSR arrays.
 static int coo_to_csr_dev(fsb_matrix* out, int nkeys, int nother, long nnz, const int* d_keys,
                           const int* d_other, const double* d_vals, cudaStream_t st) {
+  // row_ptr and the sort permutation are int32 (the reference's struct layout, csr.h:20): like the host
+  // constructor (fsb_host_csr_from_coo), refuse what they cannot index instead of truncating
+  if (nnz > (long)INT_MAX) return fsb_set_error(FSB_EINVAL, "%ld entries do not fit the int32 offsets of the CSR structure", nnz);
   out->format = FSB_FMT_CSR;
   out->nrow = nkeys;
   out->ncol = nother;
@@ -253,6 +256,43 @@ __global__ void blocked_keys_kernel(const int* __restrict__ rows, const long* __
   }
 }
 }  // namespace
+
+namespace {
+__global__ void rows_in_blocks_kernel(const int* __restrict__ rows, const long* __restrict__ blk_off, const int* __restrict__ start_row,
+                                      int nblocks, long long nnz, int* __restrict__ flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (; i < nnz; i += stride) {
+    int lo = 0, hi = nblocks;  // largest b with blk_off[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (blk_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int r = rows[i];
+    if (r < start_row[lo] || r >= start_row[lo + 1]) bad = 1;
+  }
+  if (bad) atomicAdd(flag, 1);
+}
+}  // namespace
+
+int fsb_check_rows_in_blocks(const int* d_rows, const long* d_blk_off, const int* d_start_row, int nblocks, long nnz, cudaStream_t st) {
+  if (nnz <= 0 || nblocks <= 0) return FSB_OK;
+  int* d = nullptr;
+  FSB_CUDA(cudaMalloc(&d, sizeof(int)));
+  int h = 0;
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    rows_in_blocks_kernel<<<grid_for(nnz), 256, 0, st>>>(d_rows, d_blk_off, d_start_row, nblocks, nnz, d);
+    fsb_count_launch();
+    e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fsb_cuda_error(e, "block membership validation", __FILE__, __LINE__);
+  if (h) return fsb_set_error(FSB_EINVAL, "blocked matrix: an entry's row lies outside its block's [start_row[b], start_row[b+1])");
+  return FSB_OK;
+}
 
 // Re-lay a freshly uploaded blocked COO into row-class buckets (see kernels_blocked.cu):
 // within each block, entries are stably bucketed by (local row mod 256), so a team of
@@ -455,11 +495,24 @@ extern "C" int fsb_blocked_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, l
   const int nblocks = (nrow + block_size - 1) / block_size;
   const long nkeys_l = (long)nblocks * FSB_BLOCKED_CLASSES;
   if (nkeys_l >= (1L << 24)) return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: too many row blocks (%d) for the 24-bit class key", nblocks);
-  if (order == 1) {
-    int n = 1; while (n < std::min(block_size, nrow)) n <<= 1;
-    if ((double)n * ncol >= (double)(1ull << 40)) return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: Hilbert key exceeds 40 bits");
+  if (nnz > (long)INT_MAX) return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: %ld entries do not fit the int32 class offsets", nnz);
+  // the in-block order key lives in the low 40 bits of the composite sort key: bound it for every order
+  //   order 1: row_xy2d(n, lr, c) = xy2d(n, c % n, lr) + n*n*(c / n) < n*n*ceil(ncol / n)  (>= n*n when ncol < n)
+  //   order 2: lr*ncol + c < block_size*ncol;   order 0: the entry's position < nnz
+  {
+    long long n = 1; while (n < std::min(block_size, nrow)) n <<= 1;
+    const double lim = (double)(1ull << 40);
+    const double k1 = (double)n * (double)n * (double)(((long long)ncol + n - 1) / n);
+    const double k2 = (double)std::min(block_size, nrow) * (double)ncol;
+    if ((order == 1 && k1 >= lim) || (order == 2 && k2 >= lim) || (order == 0 && (double)nnz >= lim))
+      return fsb_set_error(FSB_EINVAL, "fsb_blocked_from_coo_dev: in-block order key exceeds 40 bits (block_size %d, ncol %d)", block_size, ncol);
   }
   cudaStream_t st = fsb_default_stream();
+  // every upload path checks its indices (an out-of-range row would index past the class offsets below)
+  if (nnz > 0) {
+    FSB_TRY(fsb_check_index_range(d_rows, nnz, nrow, "row index", st));
+    FSB_TRY(fsb_check_index_range(d_cols, nnz, ncol, "column index", st));
+  }
   fsb_matrix* A = new fsb_matrix();
   A->format = FSB_FMT_BLOCKED; A->nrow = nrow; A->ncol = ncol; A->nnz = nnz; A->nblocks = nblocks; A->has_vals = d_vals != nullptr;
   A->max_block_rows = std::min(block_size, nrow);
@@ -524,6 +577,10 @@ extern "C" int fsb_cbcsr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, lon
   const long ncell = (long)nblocks * nrow;
   if (ncell >= INT32_MAX) return fsb_set_error(FSB_EINVAL, "fsb_cbcsr_from_coo_dev: nblocks*nrow exceeds the int32 cell range (cbcsr.h:41)");
   cudaStream_t st = fsb_default_stream();
+  if (nnz > 0) {   // cell keys are computed from both indices: check them first
+    FSB_TRY(fsb_check_index_range(d_rows, nnz, nrow, "row index", st));
+    FSB_TRY(fsb_check_index_range(d_cols, nnz, ncol, "column index", st));
+  }
   int* keys = nullptr;
   FSB_CUDA(cudaMalloc(&keys, (size_t)std::max<long>(nnz, 1) * 4));
   if (nnz > 0) {

@@ -390,7 +390,10 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   //    1.13 / 1.40 ms for the team-per-row kernel;
   //  * skewed rows (a row far longer than the mean, e.g. transposes of power-law matrices): the stream kernel
   //    whatever the values (230 ms -> 1.9 ms).
-  if (R == 1 && (g_algo == 0 || g_algo == 3)) {
+  // row-range aliases (chunked host products, the sharded CG's column chunks) stay on the row-local kernels: the
+  // merge-path kernel assumes row_ptr[0] == 0 and keeps per-handle tile tables
+  const bool alias = A->scratch_owner != nullptr;
+  if (R == 1 && !alias && (g_algo == 0 || g_algo == 3)) {
     bool stream = g_algo == 3 || A->has_vals;
     if (!stream) {
       int mx = 0;
@@ -401,7 +404,7 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
     if (A->avg_row_nnz <= 48.0) return run_config(A, dY, dX, 1, 2, 1, 1, 2, g_tw, st, dZ, lambda, false);
     return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st, dZ, lambda);
   }
-  if (g_algo == 3 && fsb_csr_stream_supports(R)) return stream_config(A, dY, dX, R, st, dZ, lambda);
+  if (g_algo == 3 && !alias && fsb_csr_stream_supports(R)) return stream_config(A, dY, dX, R, st, dZ, lambda);
   const int algo = (g_algo == 1) ? 1 : 2;
   // 128-bit gathers (16 lanes per 256-byte X row) beat the 256-bit form on B200 for the staged
   // kernel at R = 32 (profiles/r1b_sweep_c2_staged_vs_team.json); the 256-bit form is kept for
@@ -430,15 +433,20 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
   const bool big = algo == 2 && A->nnz >= (1 << 22);
   if (!big) return run_config(A, dY, dX, R, algo, vec, per_pass, g_g, g_tw, st, dZ, lambda, g_deep > 0);
   const bool two_pass_ok = (double)A->ncol * R * 8.0 > 126e6 && per_pass % (2 * vec) == 0 && per_pass / 2 * 8 >= 128;
-  if (A->tuned_R != R) {
+  const fsb_matrix::Tuned* tuned = fsb_tuned_find(A, R);
+  if (!tuned) {
     struct Cand { int passes; bool deep; float ms; };
     Cand cand[4];
     int nc = 0;
     for (int passes = 1; passes <= (two_pass_ok ? 2 : 1); ++passes)
       for (int deep = 0; deep <= 1; ++deep)
         if (g_deep < 0 || g_deep == deep) cand[nc++] = {passes, deep != 0, 0.f};
-    cudaEvent_t ev[8];
-    for (auto& e : ev) FSB_CUDA(cudaEventCreate(&e));
+    struct Events {   // released on every path out of this block
+      cudaEvent_t ev[8] = {};
+      ~Events() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+    } evs;
+    cudaEvent_t* ev = evs.ev;
+    for (int i = 0; i < 8; ++i) FSB_CUDA(cudaEventCreate(&ev[i]));
     int rc = FSB_OK;
     for (int k = 0; k < nc && rc == FSB_OK; ++k) {   // every candidate twice, the second run is the one timed
       rc = run_config(A, dY, dX, R, algo, vec, per_pass / cand[k].passes, g_g, g_tw, st, dZ, lambda, cand[k].deep);
@@ -452,14 +460,11 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
         cudaEventElapsedTime(&cand[k].ms, ev[2 * k], ev[2 * k + 1]);
         if (cand[k].ms < 0.99f * cand[best].ms) best = k;   // later candidates must win by 1 %
       }
-      A->tuned_R = R;
-      A->tuned_passes = cand[best].passes;
-      A->tuned_deep = cand[best].deep ? 1 : 0;
+      fsb_tuned_store(A, R, cand[best].passes, cand[best].deep ? 1 : 0);
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     return rc;
   }
-  return run_config(A, dY, dX, R, algo, vec, per_pass / A->tuned_passes, g_g, g_tw, st, dZ, lambda, A->tuned_deep != 0);
+  return run_config(A, dY, dX, R, algo, vec, per_pass / tuned->passes, g_g, g_tw, st, dZ, lambda, tuned->deep != 0);
 }
 
 int fsb_launch_csr_spmm_halves(fsb_matrix* A, double* dY, const double* dXlo, const double* dXhi, int R, cudaStream_t st,
@@ -469,7 +474,8 @@ int fsb_launch_csr_spmm_halves(fsb_matrix* A, double* dY, const double* dXlo, co
     return fsb_set_error(FSB_EINVAL, "spmm (column halves): unsupported width or alignment (R=%d)", R);
   if (A->nrow == 0) return FSB_OK;
   const int vec = 2, g = pow2_ceil(half / vec);
-  const bool deep = A->tuned_R == R ? A->tuned_deep != 0 : true;
+  const fsb_matrix::Tuned* tuned = fsb_tuned_find(A, R);
+  const bool deep = tuned ? tuned->deep != 0 : true;
   if (ready_lo) FSB_CUDA(cudaStreamWaitEvent(st, ready_lo, 0));
   FSB_TRY(fsb_launch_csr_spmm_staged(A, dY, dXlo, R, 0, half, g, vec, st, nullptr, 0.0, deep, half, 0));
   if (ready_hi) FSB_CUDA(cudaStreamWaitEvent(st, ready_hi, 0));

@@ -701,3 +701,80 @@ print("EVICT OK", e.value, b.value)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, FSB_CACHE_MAX_MB="12", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     assert r.returncode == 0 and "EVICT OK" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ round-1 review items
+def test_device_builders_validate_their_indices():
+    """fsb_blocked_from_coo_dev / fsb_cbcsr_from_coo_dev compute keys from unchecked indices: an out-of-range row used
+    to index past the class offsets.  Every builder now checks both index arrays first."""
+    import torch
+    nrow, ncol, nnz = 1000, 300, 5000
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    rows = torch.randint(0, nrow, (nnz,), device="cuda", generator=g, dtype=torch.int32)
+    cols = torch.randint(0, ncol, (nnz,), device="cuda", generator=g, dtype=torch.int32)
+    for bad_r, bad_c in ((nrow, 0), (-1, 0), (0, ncol), (0, -7)):
+        r = rows.clone(); c = cols.clone(); r[123] = bad_r if bad_r else r[123]; c[123] = bad_c if bad_c else c[123]
+        for build in (lambda: fs.DeviceMatrix.blocked_from_coo_tensors(nrow, ncol, r, c, None, 64, order=1),
+                      lambda: fs.DeviceMatrix.cbcsr_from_coo_tensors(nrow, ncol, r, c, 128)):
+            with pytest.raises(fs.FsbError) as e:
+                build()
+            assert e.value.code == 1 and "out of range" in str(e.value)
+    # in-block key guard (ADVICE low): row_xy2d keys reach n*n when ncol < n
+    one = torch.zeros(1, dtype=torch.int32, device="cuda")
+    with pytest.raises(fs.FsbError) as e:
+        fs.DeviceMatrix.blocked_from_coo_tensors(1 << 21, 1 << 10, one, one, None, 1 << 21, order=1)
+    assert "40 bits" in str(e.value)
+    with pytest.raises(fs.FsbError) as e:
+        fs.DeviceMatrix.blocked_from_coo_tensors(1 << 21, 1 << 20, one, one, None, 1 << 21, order=2)
+    assert "40 bits" in str(e.value)
+    fs.DeviceMatrix.blocked_from_coo_tensors(nrow, ncol, rows, cols, None, 64, order=1)       # still healthy
+
+
+def test_blocked_upload_validates_block_metadata():
+    nrow, ncol = 40, 10
+    A = fs.new_sbm(nrow, ncol, 6, [0, 9, 10, 25, 39, 39], [1, 2, 3, 4, 5, 6])
+    B = fs.new_bsbm(A, 10)
+    x = tvec(ncol); y = np.zeros(nrow)
+    fs.bsbm_A_mul_B(y, B, x)
+    bad = fs.new_bsbm(A, 10); bad.start_row[2] = 5           # decreasing start_row
+    with pytest.raises(fs.FsbError) as e:
+        fs.bsbm_A_mul_B(y, bad, x)
+    assert "start_row" in str(e.value)
+    bad = fs.new_bsbm(A, 10); bad.rows[0][0] = 15            # a row outside its block
+    with pytest.raises(fs.FsbError) as e:
+        fs.bsbm_A_mul_B(y, bad, x)
+    assert "outside its block" in str(e.value)
+    fs.bsbm_A_mul_B(y, B, x)
+
+
+def test_row_range_aliases_stay_on_row_local_kernels():
+    """The chunked host product passes row-range aliases (absolute row_ptr offsets) to the dispatcher; with the stream
+    kernel forced (fsb_tune_csr_algo(3), R = 2) they used to reach the merge-path kernel, which assumes row_ptr[0] == 0."""
+    nrow, ncol, nnz, R = 4_500_000, 1000, 9_000_000, 2
+    M = fs.DeviceMatrix.synth(99, 0, nnz, nrow, ncol)
+    rp, cc, _ = M.download_csr()
+    X = rhs_matrix(ncol, R).reshape(-1)
+    want = np.zeros((nrow, R)); np.add.at(want, np.repeat(np.arange(nrow), np.diff(rp)), X.reshape(ncol, R)[cc])
+    fs.check(fs.lib().fsb_tune_csr_algo(3, 0, 0))
+    try:
+        Y = np.zeros(nrow * R)
+        fs.check(fs.lib().fsb_spmm_host(M.h, Y.ctypes.data_as(C.POINTER(C.c_double)), X.ctypes.data_as(C.POINTER(C.c_double)), R))
+    finally:
+        fs.check(fs.lib().fsb_tune_csr_algo(0, 0, 0))
+    assert np.max(np.abs(Y.reshape(nrow, R) - want)) < 1e-10
+
+
+def test_autotune_remembers_every_width():
+    """A handle alternating between operand widths keeps one tuning slot per width (no re-tuning at 8x product cost)."""
+    import torch
+    M = fs.DeviceMatrix.synth(5, 0, 6_000_000, 300_000, 40_000)
+    launches = {}
+    for visit, R in enumerate((32, 8, 32, 8)):
+        X = torch.randn(40_000 * R, dtype=torch.float64, device="cuda")
+        before = fs.launch_count()
+        M.spmm(X, R); M.spmm(X, R)
+        torch.cuda.synchronize()
+        launches[(R, visit >= 2)] = fs.launch_count() - before
+        assert M.tuning()[0] == R
+    assert launches[(32, True)] <= 4 and launches[(8, True)] <= 4, f"a width was re-tuned: {launches}"
+    assert launches[(32, False)] > launches[(32, True)], f"the first visit should have timed its candidates: {launches}"
