@@ -78,7 +78,7 @@ static inline struct SparseDoubleMatrix* read_sdm(const char* filename) {
 /* global Hilbert order carrying the values (dsparse.h:96-115) */
 static inline void sort_sdm(struct SparseDoubleMatrix* A) {
   fsb_cache_drop(A->rows);
-  if (fsb_host_sort_coo_hilbert(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals)) fsb_die("sort_sdm");
+  if (fsb_sort_coo_hilbert_auto(A->nrow, A->ncol, A->nnz, A->rows, A->cols, A->vals)) fsb_die("sort_sdm");
 }
 
 struct BlockedSDM {           /* dsparse.h:119-129 */

@@ -116,7 +116,7 @@ static inline struct SparseBinaryMatrix* read_sbm(const char* filename) {
 /* global Hilbert order of the COO (sparse.h:142-161) */
 static inline void sort_sbm(struct SparseBinaryMatrix* A) {
   fsb_cache_drop(A->rows);
-  if (fsb_host_sort_coo_hilbert(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL)) fsb_die("sort_sbm");
+  if (fsb_sort_coo_hilbert_auto(A->nrow, A->ncol, A->nnz, A->rows, A->cols, NULL)) fsb_die("sort_sbm");
 }
 
 struct BlockedSBM {           /* sparse.h:163-172, sizeof 48 */

@@ -103,6 +103,16 @@ int fsb_matrix_tuning(fsb_matrix_t A, int transposed, int* R, int* passes, int* 
  * 2 = per-block row-major order (sort_bsbm_byrow sparse.h:238-256) */
 int fsb_blocked_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows,
                              const int* d_cols, const double* d_vals, int block_size, int order);
+/* global Hilbert order of a COO (sort_sbm sparse.h:142-161 / sort_sdm dsparse.h:96-115) on the device: key =
+ * xy2d(ceilPower2(max(nrow, ncol)), row, col), radix sort, coordinates decoded back with d2xy; identical to the host
+ * routine whenever coordinates are unique (equal keys keep their input order).  DEVICE arrays, sorted in place;
+ * d_vals == NULL for binary matrices. */
+int fsb_sort_coo_hilbert_dev(int nrow, int ncol, long nnz, int* d_rows, int* d_cols, double* d_vals);
+/* same on HOST arrays (upload, sort on the device, copy back): what the drop-in sort_sbm / sort_sdm call for matrices
+ * of at least FSB_SORT_DEVICE_MIN entries (default 2^20) when a device is present */
+int fsb_sort_coo_hilbert(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals);
+/* the drop-in's choice: device sort at >= FSB_SORT_DEVICE_MIN entries when a device is present, else the host routine */
+int fsb_sort_coo_hilbert_auto(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals);
 /* column-blocked binary CSR built on the device (new_cbcsr cbcsr.h:16-65) */
 int fsb_cbcsr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows,
                            const int* d_cols, int colblocksize);
@@ -319,7 +329,9 @@ int fsb_tune_csr_staged(int deep);
 
 /* Named experiment knobs (per calling thread, like every fsb_tune_* call; the environment variable
  * FSB_TUNE_<NAME> gives the default).  Known knobs: "stream_policy" (1 = L2 evict_first on the matrix
- * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads). */
+ * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads); "x_slabs" (S >= 2: the dense
+ * operand repacked into S contiguous column slabs, one pass each); "t_xblock" (1 = x-blocked transpose for A'x with
+ * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x). */
 int fsb_tune(const char* knob, int value);
 
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable

@@ -284,7 +284,7 @@ def read_sbm(filename):                                       # sparse.h:112-139
 
 def sort_sbm(A):                                              # sparse.h:142-161
     A._drop()
-    check(lib().fsb_host_sort_coo_hilbert(A.nrow, A.ncol, A.nnz, _ip(A.rows), _ip(A.cols), None))
+    check(lib().fsb_sort_coo_hilbert_auto(A.nrow, A.ncol, A.nnz, _ip(A.rows), _ip(A.cols), None))
 
 
 def A_mul_B(y, A, x):                                         # sparse.h:58-65 / dsparse.h:43-51
@@ -368,7 +368,7 @@ def read_sdm(filename):                                       # dsparse.h:64-93
 
 def sort_sdm(A):                                              # dsparse.h:96-115
     A._drop()
-    check(lib().fsb_host_sort_coo_hilbert(A.nrow, A.ncol, A.nnz, _ip(A.rows), _ip(A.cols), _dp(A.vals)))
+    check(lib().fsb_sort_coo_hilbert_auto(A.nrow, A.ncol, A.nnz, _ip(A.rows), _ip(A.cols), _dp(A.vals)))
 
 
 sdm_A_mul_B = A_mul_B                                         # dsparse.h:43-51

@@ -166,6 +166,7 @@ static void free_arrays(fsb_matrix* A) {
   cudaFree(A->start_row); cudaFree(A->blk_off); cudaFree(A->b_rows); cudaFree(A->b_cols); cudaFree(A->b_vals);
   cudaFree(A->tmp);
   if (A->T) { free_arrays(A->T); delete A->T; }
+  if (A->Tb) { free_arrays(A->Tb); delete A->Tb; }
   if (A->view) { free_arrays(A->view); delete A->view; }
 }
 
@@ -321,7 +322,8 @@ int fsb_matrix_tuning(fsb_matrix_t A, int transposed, int* R, int* passes, int* 
 
 long fsb_matrix_bytes(fsb_matrix_t A) {
   if (!A) return 0;
-  return (long)(A->bytes + (A->T ? A->T->bytes : 0) + (A->view ? A->view->bytes : 0) + A->tmp_cap + A->carry_cap);
+  return (long)(A->bytes + (A->T ? A->T->bytes : 0) + (A->Tb ? A->Tb->bytes + A->Tb->carry_cap : 0) + (A->view ? A->view->bytes : 0) +
+                A->tmp_cap + A->carry_cap + A->xpack_cap);
 }
 
 int fsb_matrix_set_row_sharded(fsb_matrix_t A, int sharded) {
@@ -407,6 +409,36 @@ static int maybe_allreduce(fsb_matrix* A, double* dY, long count, cudaStream_t s
   return FSB_OK;
 }
 
+namespace {
+// y[c] = sum over blocks b (in order) of Yv[b * ncol + c]
+__global__ void fold_blocks_kernel(const double* __restrict__ Yv, double* __restrict__ y, int ncol, int nb) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x) {
+    double s = Yv[c];
+    for (int b = 1; b < nb; ++b) s += Yv[(size_t)b * ncol + c];
+    y[c] = s;
+  }
+}
+}  // namespace
+
+// y = A'x for one right-hand side when x (nrow doubles) does not fit in L2 next to the matrix stream.  B200's 126 MB L2
+// behaves like two ~60 MB halves for a gather operand read from every SM (profiles/r2_gather_ceiling.md: 8-byte gathers
+// run at the L1 request rate from <= 64 MB and fall off above), so an 80 MB x misses 55 % of the time however the
+// loads are hinted (ncu: 5.7 GB of DRAM reads for 2.5 GB of operands).  The x-blocked transpose restores locality the
+// way cbcsr.h does on the CPU: CTAs run through the cells block by block, each block gathers from <= 32 MB of x.
+static int spmv_t_xblocked(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
+  FSB_TRY(fsb_build_transpose_xblocked(A, (size_t)std::max(1, fsb_knob("t_xblock_kb", 32 << 10)) << 10, st));
+  double* Yv = nullptr;
+  FSB_TRY(fsb_matrix_scratch(A->Tb, (size_t)A->tb_blocks * A->ncol * sizeof(double), &Yv));   // Tb's own scratch: A's may hold A x
+  FSB_TRY(fsb_launch_csr_spmm(A->Tb, Yv, dX, 1, st));
+  fold_blocks_kernel<<<std::min(148 * 8, (A->ncol + 255) / 256), 256, 0, st>>>(Yv, dY, A->ncol, A->tb_blocks);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+static bool use_xblocked_t(const fsb_matrix* A, int R) {
+  return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 48 << 10) << 10) && fsb_knob("t_xblock", 1);
+}
+
 extern "C" {
 
 int fsb_spmm_dev(fsb_matrix_t A, double* dY, const double* dX, int R, void* stream) {
@@ -420,6 +452,10 @@ int fsb_spmm_t_dev(fsb_matrix_t A, double* dY, const double* dX, int R, void* st
   if (!A || !dY || !dX) return fsb_set_error(FSB_EINVAL, "fsb_spmm_t_dev: null argument");
   if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "fsb_spmm_t_dev: CSR handle required (pass the stored transpose for blocked formats)");
   cudaStream_t st = fsb_pick_stream(stream);
+  if (use_xblocked_t(A, R)) {
+    FSB_TRY(spmv_t_xblocked(A, dY, dX, st));
+    return maybe_allreduce(A, dY, (long)A->ncol, st);
+  }
   FSB_TRY(fsb_build_transpose(A, st));
   FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dX, R, st));
   return maybe_allreduce(A, dY, (long)A->ncol * R, st);
@@ -439,6 +475,13 @@ int fsb_ata_dev(fsb_matrix_t A, double* dY, const double* dX, int R, double lamb
     return maybe_allreduce(A, dY, nF, st);
   }
   if (!dTmp) FSB_TRY(fsb_matrix_scratch(A, (size_t)A->nrow * R * sizeof(double), &dTmp));
+  if (use_xblocked_t(A, R)) {   // one right-hand side, A x too large for L2: the x-blocked transpose
+    FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
+    FSB_TRY(spmv_t_xblocked(A, dY, dTmp, st));
+    FSB_TRY(maybe_allreduce(A, dY, nF, st));
+    if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));
+    return FSB_OK;
+  }
   FSB_TRY(fsb_build_transpose(A, st));
   FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
   if (!dist) return fsb_launch_csr_spmm(A->T, dY, dTmp, R, st, lambda != 0.0 ? dX : nullptr, lambda);   // "+ lambda X" fused

@@ -72,7 +72,7 @@ int hash_threads() {
   static int n = 0;
   if (!n) {
     const char* e = getenv("FSB_HASH_THREADS");
-    int want = e ? atoi(e) : 16;
+    int want = e ? atoi(e) : 6;    // the hash shares the host with the copy threads of the product it runs beside
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0) want = std::min(want, hw);
     n = std::max(want, 1);

@@ -15,18 +15,32 @@
 #include <mutex>
 #include <thread>
 
+#include <emmintrin.h>
 #include <omp.h>
 
 #include "fsb_internal.h"
 
 namespace {
 
-constexpr int kBuffers = 4;
-constexpr size_t kBounceBytes = (size_t)32 << 20;
+// Small pieces on purpose: the DMA engine writes a piece into host memory (through the last-level cache where the
+// platform has DDIO) and a few microseconds later the copy threads read it back -- a 4 MB piece is still cache
+// resident then, a 32 MB one has been evicted to DRAM and costs the host a second trip over its memory bus.  The
+// copy out of the bounce buffer uses non-temporal stores (no read-for-ownership of the destination lines).  Measured
+// on the bench box (16 vCPUs), 2.56 GB result: 32 MB pieces + memcpy 92 ms per product against 51 ms pinned.
+constexpr int kBuffers = 6;
+size_t bounce_bytes() {          // FSB_BOUNCE_KB overrides the piece size (experiments); fixed after the first transfer
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("FSB_BOUNCE_KB");
+    v = (size_t)std::max(64L, e ? atol(e) : 4096L) << 10;
+  }
+  return v;
+}
+#define kBounceBytes (bounce_bytes())
 
 struct Ring {
-  char* buf[kBuffers] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev[kBuffers] = {nullptr, nullptr, nullptr, nullptr};
+  char* buf[kBuffers] = {};
+  cudaEvent_t ev[kBuffers] = {};
   bool ready = false;
 };
 Ring g_ring;
@@ -54,16 +68,35 @@ int copy_threads() {
   return n;
 }
 
-// bounce <-> caller memory with a few threads (explicit num_threads: torchrun exports OMP_NUM_THREADS=1)
-void host_copy(void* dst, const void* src, size_t bytes) {
+// copy with non-temporal (streaming) stores: the destination is written once and not read again by this thread
+void stream_copy(char* dst, const char* src, size_t n) {
+  size_t i = 0;
+  const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+  if (head && head <= n) { memcpy(dst, src, head); i = head; }
+  for (; i + 64 <= n; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+    _mm_stream_si128((__m128i*)(dst + i), a); _mm_stream_si128((__m128i*)(dst + i + 16), b);
+    _mm_stream_si128((__m128i*)(dst + i + 32), c); _mm_stream_si128((__m128i*)(dst + i + 48), d);
+  }
+  if (i < n) memcpy(dst + i, src + i, n - i);
+  _mm_sfence();
+}
+
+// bounce <-> caller memory with a few threads (explicit num_threads: torchrun exports OMP_NUM_THREADS=1);
+// streaming = true for bounce -> caller (the D2H leg)
+void host_copy(void* dst, const void* src, size_t bytes, bool streaming) {
   const int nt = copy_threads();
-  if (nt == 1 || bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
-  const size_t piece = (size_t)1 << 20;
+  const size_t piece = (size_t)256 << 10;
+  if (nt == 1 || bytes < 2 * piece) {
+    if (streaming) stream_copy((char*)dst, (const char*)src, bytes); else memcpy(dst, src, bytes);
+    return;
+  }
   const long np = (long)((bytes + piece - 1) / piece);
 #pragma omp parallel for num_threads(nt) schedule(static)
   for (long p = 0; p < np; ++p) {
-    const size_t off = (size_t)p * piece;
-    memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off));
+    const size_t off = (size_t)p * piece, n = std::min(piece, bytes - off);
+    if (streaming) stream_copy((char*)dst + off, (const char*)src + off, n); else memcpy((char*)dst + off, (const char*)src + off, n);
   }
 }
 
@@ -92,7 +125,7 @@ int fsb_h2d(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   for (size_t off = 0; off < bytes; off += kBounceBytes, k = (k + 1) % kBuffers) {
     const size_t n = std::min(kBounceBytes, bytes - off);
     if (off >= kBuffers * kBounceBytes) FSB_CUDA(cudaEventSynchronize(g_ring.ev[k]));   // the copy that last used this buffer
-    host_copy(g_ring.buf[k], (const char*)src + off, n);
+    host_copy(g_ring.buf[k], (const char*)src + off, n, false);
     FSB_CUDA(cudaMemcpyAsync((char*)dst + off, g_ring.buf[k], n, cudaMemcpyHostToDevice, st));
     FSB_CUDA(cudaEventRecord(g_ring.ev[k], st));
   }
@@ -144,7 +177,7 @@ int fsb_d2h_segments(int nseg, void* const* dst, const void* const* src, const s
     const int k = (int)(p % kBuffers);
     e = cudaEventSynchronize(g_ring.ev[k]);
     if (e != cudaSuccess) break;
-    host_copy(pc[p].h, g_ring.buf[k], pc[p].n);
+    host_copy(pc[p].h, g_ring.buf[k], pc[p].n, true);
     if (p + kBuffers < np) e = enqueue(p + kBuffers);
   }
   if (e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_d2h_segments", __FILE__, __LINE__);

@@ -29,6 +29,11 @@ struct fsb_matrix {
   int max_block_rows = 0;
   // lazily built, cached transpose (CSR handles only)
   fsb_matrix* T = nullptr;
+  // lazily built x-BLOCKED transpose for one right-hand side (fsb_build_transpose_xblocked): the entries of A' grouped
+  // by contiguous blocks of A's rows, i.e. a CSR with tb_blocks * ncol "cell" rows (cell = block * ncol + column of A),
+  // so that the slice of x a wave of CTAs gathers from stays L2-resident -- cbcsr.h's column blocking applied to A'
+  fsb_matrix* Tb = nullptr;
+  int tb_blocks = 0;
   // lazily built CSR view of a blocked / column-blocked matrix (same entries, stable by row, so
   // every row keeps its stored order); products default to the CSR kernels through it
   fsb_matrix* view = nullptr;
@@ -157,6 +162,7 @@ int fsb_check_rows_in_blocks(const int* d_rows, const long* d_blk_off, const int
 int fsb_build_csr_from_coo_dev(fsb_matrix* out, int nrow, int ncol, long nnz, const int* d_rows,
                                const int* d_cols, const double* d_vals, cudaStream_t st);
 int fsb_build_transpose(fsb_matrix* A, cudaStream_t st);   // fills A->T
+int fsb_build_transpose_xblocked(fsb_matrix* A, size_t block_bytes, cudaStream_t st);   // fills A->Tb / A->tb_blocks
 int fsb_build_csr_view(fsb_matrix* A, cudaStream_t st);    // fills A->view (BLOCKED / CBCSR)
 int fsb_stable_perm_by_key(const int* d_keys, int nkeys, long n, int* d_perm, int* d_ptr, cudaStream_t st);
 #define FSB_BLOCKED_CLASSES 256

@@ -8,6 +8,8 @@
 //     the transposed COO: bench_a_mul_b.c:273-274, test_sparse.c:564-565).
 // (3) Counter-based synthetic COO generator shared bit-for-bit with the host
 //     (SURVEY 8d): entry j is a pure function of (seed, j).
+#include <stdlib.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fsb_internal.h"
@@ -414,6 +416,48 @@ int fsb_build_transpose(fsb_matrix* A, cudaStream_t st) {
   return FSB_OK;
 }
 
+namespace {
+__global__ void xblock_key_kernel(const int* __restrict__ rowid, const int* __restrict__ cols, long long nnz, int rows_per_block, int ncol,
+                                  int* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) keys[i] = (rowid[i] / rows_per_block) * ncol + cols[i];
+}
+}  // namespace
+
+// x-blocked transpose (see fsb_internal.h): cell = (row of A / rows_per_block) * ncol + column of A; stable sort by
+// cell, so inside a cell the entries keep the CSR order (increasing row of A) -- the same order the plain transpose
+// gives each of its rows, cut at the block boundaries.
+int fsb_build_transpose_xblocked(fsb_matrix* A, size_t block_bytes, cudaStream_t st) {
+  if (A->Tb) return FSB_OK;
+  if (A->format != FSB_FMT_CSR) return fsb_set_error(FSB_EINVAL, "x-blocked transpose: CSR handles only");
+  const size_t xbytes = (size_t)A->nrow * 8;
+  const int nb = (int)std::max<size_t>(1, (xbytes + block_bytes - 1) / block_bytes);
+  const int rpb = (A->nrow + nb - 1) / nb;
+  if ((long)nb * A->ncol >= (long)INT_MAX) return fsb_set_error(FSB_EINVAL, "x-blocked transpose: %d blocks x %d columns exceed the int32 cell range", nb, A->ncol);
+  const size_t n1 = (size_t)std::max<long>(A->nnz, 1);
+  int *rowid = nullptr, *keys = nullptr;
+  FSB_CUDA(cudaMalloc(&rowid, n1 * sizeof(int)));
+  cudaError_t e = cudaMalloc(&keys, n1 * sizeof(int));
+  if (e != cudaSuccess) { cudaFree(rowid); return fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__); }
+  if (A->nnz > 0) {
+    expand_rows_kernel<<<grid_for(A->nnz), 256, 0, st>>>(A->row_ptr, A->nrow, A->nnz, rowid);
+    xblock_key_kernel<<<grid_for(A->nnz), 256, 0, st>>>(rowid, A->cols, A->nnz, rpb, A->ncol, keys);
+    fsb_count_launch(2);
+  }
+  fsb_matrix* T = new fsb_matrix();
+  int rc = coo_to_csr_dev(T, nb * A->ncol, A->nrow, A->nnz, keys, rowid, A->vals, st);
+  cudaFree(rowid); cudaFree(keys);
+  if (rc != FSB_OK) {
+    cudaFree(T->row_ptr); cudaFree(T->cols); cudaFree(T->vals);
+    delete T;
+    return rc;
+  }
+  A->Tb = T;
+  A->tb_blocks = nb;
+  return FSB_OK;
+}
+
 // ---------------------------------------------------------------- device-side builders for the blocked formats
 namespace {
 
@@ -565,6 +609,125 @@ extern "C" int fsb_blocked_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, l
   A->bytes = ((size_t)nkeys + 1) * 4 + ((size_t)nblocks + 1) * 12 + n1 * (d_vals ? 16 : 8);
   *out = A;
   return FSB_OK;
+}
+
+// ---------------------------------------------------------------- global Hilbert order of a COO (sort_sbm / sort_sdm)
+namespace {
+__device__ __forceinline__ void dev_d2xy(int n, long long d, int* xo, int* yo) {   // hilbert.h:30-42, device twin
+  int x = 0, y = 0;
+  long long t = d;
+  for (int s = 1; s < n; s *= 2) {
+    const int rx = (int)(1 & (t / 2));
+    const int ry = (int)(1 & (t ^ rx));
+    if (!ry) {
+      if (rx) { x = s - 1 - x; y = s - 1 - y; }
+      const int w = x; x = y; y = w;
+    }
+    x += s * rx;
+    y += s * ry;
+    t /= 4;
+  }
+  *xo = x;
+  *yo = y;
+}
+
+__global__ void hilbert_key_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long nnz, int n,
+                                   unsigned long long* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) keys[i] = (unsigned long long)dev_xy2d(n, rows[i], cols[i]);   // sparse.h:150-153
+}
+
+__global__ void hilbert_decode_kernel(const unsigned long long* __restrict__ keys, long long nnz, int n, int* __restrict__ rows,
+                                      int* __restrict__ cols) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) dev_d2xy(n, (long long)keys[i], &rows[i], &cols[i]);           // sparse.h:155-158
+}
+}  // namespace
+
+// sort_sbm (sparse.h:142-161) / sort_sdm (dsparse.h:96-115) on the device: key = xy2d(n, row, col) with
+// n = ceilPower2(max(nrow, ncol)), ascending sort, coordinates decoded back from the sorted keys with d2xy -- the
+// reference's three steps, with a radix sort on the 2 log2(n) significant key bits in place of the serial quicksort.
+// The result is the unique ascending key order; entries with EQUAL coordinates are interchangeable for binary
+// matrices, and for valued ones the radix sort keeps their input order (the reference's quickSortD leaves it
+// unspecified).  d_rows / d_cols / d_vals are sorted in place.
+extern "C" int fsb_sort_coo_hilbert_dev(int nrow, int ncol, long nnz, int* d_rows, int* d_cols, double* d_vals) {
+  FSB_TRY(fsb_require_device());
+  if (nrow < 0 || ncol < 0 || nnz < 0 || (nnz > 0 && (!d_rows || !d_cols))) return fsb_set_error(FSB_EINVAL, "fsb_sort_coo_hilbert_dev: bad arguments");
+  if (nnz == 0) return FSB_OK;
+  cudaStream_t st = fsb_default_stream();
+  FSB_TRY(fsb_check_index_range(d_rows, nnz, nrow, "row index", st));
+  FSB_TRY(fsb_check_index_range(d_cols, nnz, ncol, "column index", st));
+  const int n = fsb_host_ceil_pow2(std::max(nrow, ncol));
+  int key_bits = 2;
+  while ((1LL << (key_bits / 2)) < n) key_bits += 2;          // keys < n*n
+  unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+  double* vals_sorted = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cudaError_t e = cudaMalloc(&keys, (size_t)nnz * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&keys_sorted, (size_t)nnz * 8);
+  if (e == cudaSuccess && d_vals) e = cudaMalloc(&vals_sorted, (size_t)nnz * 8);
+  if (e == cudaSuccess) {
+    hilbert_key_kernel<<<grid_for(nnz), 256, 0, st>>>(d_rows, d_cols, nnz, n, keys);
+    fsb_count_launch();
+    if (d_vals) {
+      cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, d_vals, vals_sorted, (long long)nnz, 0, key_bits, st);
+      e = cudaMalloc(&tmp, tmp_bytes);
+      if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, d_vals, vals_sorted, (long long)nnz, 0, key_bits, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_vals, vals_sorted, (size_t)nnz * 8, cudaMemcpyDeviceToDevice, st);
+    } else {
+      cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys_sorted, (long long)nnz, 0, key_bits, st);
+      e = cudaMalloc(&tmp, tmp_bytes);
+      if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys_sorted, (long long)nnz, 0, key_bits, st);
+    }
+    fsb_count_launch(2 + key_bits / 8);
+  }
+  if (e == cudaSuccess) {
+    hilbert_decode_kernel<<<grid_for(nnz), 256, 0, st>>>(keys_sorted, nnz, n, d_rows, d_cols);
+    fsb_count_launch();
+    e = cudaStreamSynchronize(st);
+  }
+  cudaFree(keys); cudaFree(keys_sorted); cudaFree(vals_sorted); cudaFree(tmp);
+  if (e != cudaSuccess) return fsb_cuda_error(e, "fsb_sort_coo_hilbert_dev", __FILE__, __LINE__);
+  return FSB_OK;
+}
+
+// host arrays: upload, sort on the device, copy back (what the drop-in sort_sbm / sort_sdm call for large matrices)
+extern "C" int fsb_sort_coo_hilbert(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals) {
+  FSB_TRY(fsb_require_device());
+  if (nnz < 0 || (nnz > 0 && (!rows || !cols))) return fsb_set_error(FSB_EINVAL, "fsb_sort_coo_hilbert: bad arguments");
+  if (nnz == 0) return FSB_OK;
+  cudaStream_t st = fsb_default_stream();
+  int *dr = nullptr, *dc = nullptr;
+  double* dv = nullptr;
+  cudaError_t e = cudaMalloc(&dr, (size_t)nnz * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&dc, (size_t)nnz * 4);
+  if (e == cudaSuccess && vals) e = cudaMalloc(&dv, (size_t)nnz * 8);
+  int rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
+  if (rc == FSB_OK) rc = fsb_h2d(dr, rows, (size_t)nnz * 4, st);
+  if (rc == FSB_OK) rc = fsb_h2d(dc, cols, (size_t)nnz * 4, st);
+  if (rc == FSB_OK && vals) rc = fsb_h2d(dv, vals, (size_t)nnz * 8, st);
+  if (rc == FSB_OK) rc = fsb_sort_coo_hilbert_dev(nrow, ncol, nnz, dr, dc, dv);
+  if (rc == FSB_OK) rc = fsb_d2h(rows, dr, (size_t)nnz * 4, st);
+  if (rc == FSB_OK) rc = fsb_d2h(cols, dc, (size_t)nnz * 4, st);
+  if (rc == FSB_OK && vals) rc = fsb_d2h(vals, dv, (size_t)nnz * 8, st);
+  if (rc == FSB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "fsb_sort_coo_hilbert", __FILE__, __LINE__);
+  cudaFree(dr); cudaFree(dc); cudaFree(dv);
+  return rc;
+}
+
+// what the drop-in sort_sbm / sort_sdm call: the device path for large matrices when a device is present, the
+// bit-exact serial host routine otherwise (sorting is construction, not the product path: both give the same order)
+extern "C" int fsb_sort_coo_hilbert_auto(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals) {
+  static long min_dev = -1;
+  if (min_dev < 0) {
+    const char* e = getenv("FSB_SORT_DEVICE_MIN");
+    min_dev = e ? atol(e) : (1L << 20);
+  }
+  if (nnz >= min_dev && fsb_device_count() > 0) return fsb_sort_coo_hilbert(nrow, ncol, nnz, rows, cols, vals);
+  return fsb_host_sort_coo_hilbert(nrow, ncol, nnz, rows, cols, vals);
 }
 
 // Column-blocked binary CSR built on the device (new_cbcsr cbcsr.h:16-65): stable sort by cell.

@@ -778,3 +778,74 @@ def test_autotune_remembers_every_width():
         assert M.tuning()[0] == R
     assert launches[(32, True)] <= 4 and launches[(8, True)] <= 4, f"a width was re-tuned: {launches}"
     assert launches[(32, False)] > launches[(32, True)], f"the first visit should have timed its candidates: {launches}"
+
+
+@pytest.mark.parametrize("with_vals", [False, True])
+def test_xblocked_transposed_spmv_matches_the_plain_transpose(with_vals):
+    """y = A'x with one right-hand side switches to the x-blocked transpose when x outgrows L2 (fsb_capi.cu
+    spmv_t_xblocked).  Forced here on a small matrix with many blocks (ragged last block, empty cells, a 3000-entry
+    column): same result as the plain cached transpose and as the oracle's COO scatter (sparse.h:68-75)."""
+    import torch
+    nrow, ncol, nnz = 100_003, 2_000, 900_000
+    rows, cols, vals = fs.synth_coo_host(77, 1, nnz, nrow, ncol, with_vals=with_vals)
+    M = fs.DeviceMatrix.from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(),
+                                         torch.from_numpy(vals).cuda() if with_vals else None)
+    x = tvec(nrow)
+    xd = torch.from_numpy(x).cuda()
+    L = fs.lib()
+    fs.check(L.fsb_tune(b"t_xblock", 0))
+    plain = M.spmm_t(xd, 1).cpu().numpy()
+    fs.check(L.fsb_tune(b"t_xblock", 1)); fs.check(L.fsb_tune(b"t_xblock_min_kb", 1)); fs.check(L.fsb_tune(b"t_xblock_kb", 16))
+    try:
+        blocked = M.spmm_t(xd, 1).cpu().numpy()
+        z = M.ata(torch.from_numpy(tvec(ncol)).cuda(), 1, lam=0.5).cpu().numpy()
+    finally:
+        fs.check(L.fsb_tune(b"t_xblock_min_kb", 48 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
+    want = oracle.coo_mul(nrow, rows, cols, vals, x, transpose=True, ncol=ncol)
+    scale = 2.0 * float(np.bincount(cols, minlength=ncol).max())
+    assert_close(blocked, want, scale=scale, what="x-blocked A'x vs oracle")
+    assert_close(blocked, plain, scale=scale, what="x-blocked A'x vs plain transpose")
+    # A'(A x) + lambda x through the same path
+    xc = tvec(ncol)
+    ax = oracle.coo_mul(nrow, rows, cols, vals, xc)
+    want2 = oracle.coo_mul(nrow, rows, cols, vals, ax, transpose=True, ncol=ncol) + 0.5 * xc
+    assert_close(z, want2, scale=scale * scale, what="A'(A x) + lambda x via the x-blocked transpose")
+
+
+@pytest.mark.parametrize("with_vals", [False, True])
+def test_device_global_hilbert_sort_matches_host(with_vals):
+    """sort_sbm / sort_sdm on the device: bit-exact against the host routine (itself pinned to the
+    reference's goldens) on unique coordinates, values carried; duplicates keep their input order; the drop-in
+    entry point picks the device path above FSB_SORT_DEVICE_MIN entries."""
+    import torch
+    rng = np.random.default_rng(11)
+    for nrow, ncol, nnz in [(100, 50, 504), (70_000, 131_072, 400_000), (5, 3, 15), (1, 1, 1)]:
+        flat = rng.choice(nrow * ncol, size=nnz, replace=False)            # unique coordinates
+        rows = (flat // ncol).astype(np.int32); cols = (flat % ncol).astype(np.int32)
+        vals = rng.random(nnz) if with_vals else None
+        hr, hc = rows.copy(), cols.copy(); hv = vals.copy() if with_vals else None
+        fs.check(fs.lib().fsb_host_sort_coo_hilbert(nrow, ncol, nnz, fs.api._ip(hr), fs.api._ip(hc), fs.api._dp(hv)))
+        dr, dc = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+        dv = torch.from_numpy(vals).cuda() if with_vals else None
+        fs.check(fs.lib().fsb_sort_coo_hilbert_dev(nrow, ncol, nnz, dr.data_ptr(), dc.data_ptr(), dv.data_ptr() if with_vals else None))
+        assert np.array_equal(dr.cpu().numpy(), hr) and np.array_equal(dc.cpu().numpy(), hc)
+        if with_vals:
+            assert np.array_equal(dv.cpu().numpy(), hv)
+        # host-array entry point (upload / sort / download)
+        ar, ac = rows.copy(), cols.copy(); av = vals.copy() if with_vals else None
+        fs.check(fs.lib().fsb_sort_coo_hilbert(nrow, ncol, nnz, fs.api._ip(ar), fs.api._ip(ac), fs.api._dp(av)))
+        assert np.array_equal(ar, hr) and np.array_equal(ac, hc) and (not with_vals or np.array_equal(av, hv))
+        # keys strictly increasing (test_sparse.c:283-289)
+        n = fs.ceilPower2(max(nrow, ncol))
+        keys = np.array([fs.xy2d(n, int(r), int(c)) for r, c in zip(hr[:2000], hc[:2000])])
+        assert np.all(np.diff(keys) > 0)
+    # duplicates: binary entries are interchangeable; valued duplicates keep their input order (stable radix sort)
+    rows = np.array([3, 1, 3, 3, 0], np.int32); cols = np.array([2, 1, 2, 2, 0], np.int32); vals = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    dr, dc, dv = torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), torch.from_numpy(vals).cuda()
+    fs.check(fs.lib().fsb_sort_coo_hilbert_dev(4, 3, 5, dr.data_ptr(), dc.data_ptr(), dv.data_ptr()))
+    r, c, v = dr.cpu().numpy(), dc.cpu().numpy(), dv.cpu().numpy()
+    dup = (r == 3) & (c == 2)
+    assert dup.sum() == 3 and list(v[dup]) == [1.0, 3.0, 4.0]
+    with pytest.raises(fs.FsbError):
+        bad = torch.tensor([0, 9], dtype=torch.int32, device="cuda")
+        fs.check(fs.lib().fsb_sort_coo_hilbert_dev(4, 3, 2, bad.data_ptr(), bad.data_ptr(), None))
