@@ -329,7 +329,7 @@ int fsb_tune_csr_staged(int deep);
 
 /* Named experiment knobs (per calling thread, like every fsb_tune_* call; the environment variable
  * FSB_TUNE_<NAME> gives the default).  Known knobs: "stream_policy" (1 = L2 evict_first on the matrix
- * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads); "x_slabs" (S >= 2: the dense
+ * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads, the default); "x_slabs" (S >= 2: the dense
  * operand repacked into S contiguous column slabs, one pass each); "t_xblock" (1 = x-blocked transpose for A'x with
  * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x). */
 int fsb_tune(const char* knob, int value);

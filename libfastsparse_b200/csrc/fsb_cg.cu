@@ -161,6 +161,7 @@ struct CgShardWork {
   long F = 0, Fc = 0, s = 0, Fp = 0, nloc = 0;
   double *Pfull = nullptr, *KPpart = nullptr, *Xl = nullptr, *Rl = nullptr, *Pl = nullptr, *KPl = nullptr, *tmp = nullptr;
   double* Psend = nullptr;          // column halves of P_loc, the send buffers of the split all-gather
+  fsb_p2p* p2p = nullptr;           // Pfull lives in a peer-mapped buffer: P is all-gathered by direct NVLink stores
   double *G1 = nullptr, *G2 = nullptr, *PtKP = nullptr, *Alpha = nullptr, *Psi = nullptr, *norm = nullptr, *inorm = nullptr;
   double *partial = nullptr;
   int *status = nullptr, *h_status = nullptr;
@@ -170,6 +171,7 @@ struct CgShardWork {
   void release() {
     cudaFree(Psend);
     for (cudaEvent_t e : {ev_p, ev_lo, ev_hi}) if (e) cudaEventDestroy(e);
+    if (p2p) { fsb_p2p_destroy(p2p); p2p = nullptr; Pfull = nullptr; }
     cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
     cudaFree(G1); cudaFree(G2); cudaFree(PtKP); cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial);
     cudaFree(status);
@@ -197,7 +199,10 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   w.G = fsb_comm_size(); w.rank = fsb_comm_rank(); w.F = F;
   shard_layout(F, R, w.G, &w.C, &w.s, &w.Fc, &w.Fp, &w.nloc);
   const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8, rr = (size_t)R * R * 8;
-  FSB_CUDA(cudaMalloc(&w.Pfull, full)); FSB_CUDA(cudaMalloc(&w.KPpart, full));
+  // Pfull in peer-mapped memory when CUDA IPC works between the ranks (knob "cg_p2p", default on); plain memory + NCCL otherwise
+  if (fsb_knob("cg_p2p", 1) && w.G > 1 && fsb_p2p_create(&w.p2p, full, fsb_default_stream()) == FSB_OK) w.Pfull = (double*)fsb_p2p_local(w.p2p);
+  else { w.p2p = nullptr; FSB_CUDA(cudaMalloc(&w.Pfull, full)); }
+  FSB_CUDA(cudaMalloc(&w.KPpart, full));
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
   FSB_CUDA(cudaMalloc(&w.Psend, loc));
   FSB_CUDA(cudaMalloc(&w.tmp, std::max<size_t>((size_t)Nloc * R, 1) * 8));
@@ -232,6 +237,7 @@ int shard_gram(CgShardWork& w, double* G, const double* Xa, const double* Xb, in
 
 // all-gather the local slices of every chunk of a sharded vector into the replicated layout
 int shard_allgather(CgShardWork& w, double* full, const double* loc, int R, cudaStream_t st) {
+  if (w.p2p && full == w.Pfull) return fsb_p2p_allgather_chunks(w.p2p, loc, w.C, w.s * R, st);   // direct peer stores
   FSB_TRY(fsb_comm_group_start());   // the C per-chunk gathers go out as one fused NCCL launch
   int rc = FSB_OK;
   for (int c = 0; c < w.C && rc == FSB_OK; ++c)
@@ -393,6 +399,7 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   }
   const int it = w.h_status[2];
   for (auto& e : pe) if (e) cudaEventDestroy(e);
+  if (w.p2p) FSB_TRY(fsb_p2p_check(w.p2p, st));
   // X = X_loc diag(norm), gathered into the replicated result (through the partial buffer: padded rows)
   for (int c = 0; c < w.C; ++c) FSB_TRY(fsb_dense_scale_cols(w.Xl + (size_t)c * w.s * R, w.norm, w.s, R, st));
   FSB_TRY(shard_allgather(w, w.KPpart, w.Xl, R, st));

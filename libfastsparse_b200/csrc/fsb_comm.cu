@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "fsb_internal.h"
@@ -168,3 +169,212 @@ int fsb_partition_rows(int nrow, const int* row_ptr, int nparts, int* bounds) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Peer-memory collectives over NVLink / NVSwitch (one process per GPU on one node).
+//
+// A symmetric buffer is cudaMalloc'ed by every rank and mapped into every other rank's address space through CUDA IPC
+// (the unique ids of the handles travel through one NCCL all-gather).  On top of it:
+//   fsb_p2p_allgather_chunks -- the all-gather of the block-CG search directions P: every rank STORES its slices
+//     straight into the replicated buffer of all G ranks (peer stores over NVLink, 16 bytes per thread), then publishes
+//     an epoch flag to each peer (release at system scope after the last CTA's stores); a one-thread wait kernel on the
+//     consumer's stream acquires the G flags before the product that reads P starts.  No staging copies, no
+//     intermediate protocol buffers: the bytes cross the switch once, at the rate the SMs can push them.
+// Safe reuse without double buffering: a rank can only reach its next push after the reduce-scatter of the current
+// iteration, which needs every rank's A'(A P) partial, i.e. every rank has finished reading the previous P.
+// The wait kernel gives up after ~4 s (a peer died) and raises a device-side error flag instead of hanging the GPU.
+namespace {
+
+constexpr int kMaxPeers = 8;
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct PushArgs {
+  double2* dst[kMaxPeers];                  // replicated buffer of every rank (this rank's own included)
+  unsigned long long* flags[kMaxPeers];     // flag array of every rank: flags[g][src_rank]
+};
+
+// src: this rank's local slices [C][slice2] (double2 units); destination offset of slice (c, rank): c*chunk2 + rank*slice2
+__global__ void __launch_bounds__(256) p2p_push_kernel(const double2* __restrict__ src, PushArgs a, long long slice2, long long chunk2, int C,
+                                                       int G, int rank, unsigned long long epoch, unsigned int* __restrict__ counter) {
+  const int g = blockIdx.y;
+  double2* __restrict__ dst = a.dst[g];
+  const long long n = (long long)C * slice2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i / slice2, k = i - c * slice2;
+    dst[c * chunk2 + (long long)rank * slice2 + k] = src[i];
+  }
+  // the last CTA to finish publishes the epoch: every CTA's stores -> system fence -> counter; last CTA -> fence -> flags
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    last = atomicAdd(counter, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < G) st_release_sys(a.flags[threadIdx.x] + rank, epoch);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// one warp: lane g waits for rank g's flag; err[0] is set when a peer never shows up
+__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int G, unsigned long long epoch, int* __restrict__ err) {
+  const int g = threadIdx.x;
+  if (g >= G) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flags + g) < epoch) {
+    if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }    // ~4 s at 2 GHz
+    __nanosleep(64);
+  }
+}
+
+}  // namespace
+
+struct fsb_p2p {
+  int G = 1, rank = 0;
+  size_t bytes = 0;
+  void* local = nullptr;
+  void* peer[kMaxPeers] = {};               // peer[g]: rank g's buffer mapped here (peer[rank] == local)
+  unsigned long long* flags = nullptr;      // [kMaxPeers] at the head of this rank's flag page
+  unsigned long long* peer_flags[kMaxPeers] = {};
+  unsigned int* counter = nullptr;
+  int* err = nullptr;
+  unsigned long long epoch = 0;
+};
+
+namespace {
+// every rank contributes one IPC handle; out[g] = rank g's allocation mapped into this process
+int exchange_ipc(void* mine, void* out[kMaxPeers], cudaStream_t st) {
+  cudaIpcMemHandle_t h;
+  int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+  if (!ok) cudaGetLastError();
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  constexpr int kWords = 16;                // 64 bytes of handle + status, in doubles
+  double hbuf[kWords] = {};
+  memcpy(hbuf, &h, 64);
+  hbuf[8] = ok;
+  double *dsend = nullptr, *drecv = nullptr;
+  FSB_CUDA(cudaMalloc(&dsend, kWords * 8));
+  cudaError_t e = cudaMalloc(&drecv, (size_t)kWords * 8 * g_nranks);
+  int rc = e == cudaSuccess ? FSB_OK : fsb_cuda_error(e, "cudaMalloc", __FILE__, __LINE__);
+  double all[kWords * kMaxPeers] = {};
+  if (rc == FSB_OK) {
+    e = cudaMemcpyAsync(dsend, hbuf, sizeof hbuf, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = fsb_comm_allgather(dsend, drecv, kWords, st);
+    if (e == cudaSuccess && rc == FSB_OK) e = cudaMemcpyAsync(all, drecv, (size_t)kWords * 8 * g_nranks, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && rc == FSB_OK) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "IPC handle exchange", __FILE__, __LINE__);
+  }
+  cudaFree(dsend); cudaFree(drecv);
+  FSB_TRY(rc);
+  for (int g = 0; g < g_nranks; ++g)
+    if (all[g * kWords + 8] != 1.0) return fsb_set_error(FSB_ENCCL, "peer memory: rank %d could not export an IPC handle", g);
+  for (int g = 0; g < g_nranks; ++g) {
+    if (g == g_rank) { out[g] = mine; continue; }
+    cudaIpcMemHandle_t ph;
+    memcpy(&ph, &all[g * kWords], 64);
+    e = cudaIpcOpenMemHandle(&out[g], ph, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fsb_set_error(FSB_ENCCL, "peer memory: cannot map rank %d's buffer (%s)", g, cudaGetErrorString(e));
+    }
+  }
+  return FSB_OK;
+}
+}  // namespace
+
+// Collective (every rank, same size, same order).  On failure on ANY rank every rank returns an error (the status
+// is agreed through an allreduce) and the caller keeps using NCCL.
+int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
+  *out = nullptr;
+  if (!fsb_comm_active() || g_nranks > kMaxPeers) return fsb_set_error(FSB_ENCCL, "peer memory: needs an active communicator of at most %d ranks", kMaxPeers);
+  fsb_p2p* p = new fsb_p2p();
+  p->G = g_nranks; p->rank = g_rank; p->bytes = bytes;
+  int rc = FSB_OK;
+  void* flagpage = nullptr;
+  cudaError_t e = cudaMalloc(&p->local, std::max<size_t>(bytes, 256));
+  if (e == cudaSuccess) e = cudaMalloc(&flagpage, 4096);
+  if (e == cudaSuccess) e = cudaMemsetAsync(flagpage, 0, 4096, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaGetLastError(); rc = FSB_ECUDA; }
+  void* pf[kMaxPeers] = {};
+  int rc1 = rc == FSB_OK ? exchange_ipc(p->local, p->peer, st) : rc;
+  int rc2 = rc == FSB_OK ? exchange_ipc(flagpage, pf, st) : rc;     // both exchanges always run: they are collective
+  if (rc == FSB_OK) rc = rc1 != FSB_OK ? rc1 : rc2;
+  // agree on the outcome
+  double flag = rc == FSB_OK ? 0.0 : 1.0, *dflag = nullptr;
+  if (cudaMalloc(&dflag, 8) == cudaSuccess) {
+    cudaMemcpyAsync(dflag, &flag, 8, cudaMemcpyHostToDevice, st);
+    fsb_allreduce_sum_dev(dflag, 1, (void*)st);
+    cudaMemcpyAsync(&flag, dflag, 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dflag);
+  }
+  if (flag != 0.0 || rc != FSB_OK) {
+    for (int g = 0; g < p->G; ++g) {
+      if (g != p->rank && p->peer[g]) cudaIpcCloseMemHandle(p->peer[g]);
+      if (g != p->rank && pf[g]) cudaIpcCloseMemHandle(pf[g]);
+    }
+    cudaFree(p->local); cudaFree(flagpage);
+    delete p;
+    return rc != FSB_OK ? rc : fsb_set_error(FSB_ENCCL, "peer memory: another rank could not map the buffers");
+  }
+  p->flags = (unsigned long long*)flagpage;
+  for (int g = 0; g < p->G; ++g) p->peer_flags[g] = (unsigned long long*)pf[g];
+  p->counter = (unsigned int*)((char*)flagpage + 2048);
+  p->err = (int*)((char*)flagpage + 2048 + 64);
+  *out = p;
+  return FSB_OK;
+}
+
+void fsb_p2p_destroy(fsb_p2p* p) {
+  if (!p) return;
+  cudaDeviceSynchronize();
+  for (int g = 0; g < p->G; ++g) {
+    if (g == p->rank) continue;
+    if (p->peer[g]) cudaIpcCloseMemHandle(p->peer[g]);
+    if (p->peer_flags[g]) cudaIpcCloseMemHandle(p->peer_flags[g]);
+  }
+  cudaFree(p->local);
+  cudaFree(p->flags);
+  delete p;
+}
+
+void* fsb_p2p_local(fsb_p2p* p) { return p->local; }
+
+// all-gather of C chunks: rank r's slice of chunk c (slice doubles at loc + c*slice) lands at offset c*G*slice + r*slice of
+// EVERY rank's buffer.  Returns after enqueueing push + wait on st; the data is complete for kernels that follow on st.
+int fsb_p2p_allgather_chunks(fsb_p2p* p, const double* loc, int C, long slice, cudaStream_t st) {
+  if (slice % 2 || ((uintptr_t)loc & 15)) return fsb_set_error(FSB_EINVAL, "peer all-gather: slices must be 16-byte aligned");
+  if ((size_t)C * p->G * slice * 8 > p->bytes) return fsb_set_error(FSB_EINVAL, "peer all-gather: buffer too small");
+  PushArgs a;
+  for (int g = 0; g < kMaxPeers; ++g) { a.dst[g] = g < p->G ? (double2*)p->peer[g] : nullptr; a.flags[g] = g < p->G ? p->peer_flags[g] : nullptr; }
+  const unsigned long long epoch = ++p->epoch;
+  const long long n2 = (long long)C * slice / 2;
+  const int bx = (int)std::max<long long>(1, std::min<long long>((n2 + 255) / 256, (148 * 4) / p->G + 1));
+  dim3 grid(bx, p->G);
+  p2p_push_kernel<<<grid, 256, 0, st>>>((const double2*)loc, a, slice / 2, (long long)p->G * slice / 2, C, p->G, p->rank, epoch, p->counter);
+  FSB_KERNEL_CHECK();
+  p2p_wait_kernel<<<1, 32, 0, st>>>(p->flags, p->G, epoch, p->err);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+// non-zero when a wait kernel timed out (a peer never published its epoch)
+int fsb_p2p_check(fsb_p2p* p, cudaStream_t st) {
+  int h = 0;
+  FSB_CUDA(cudaMemcpyAsync(&h, p->err, sizeof h, cudaMemcpyDeviceToHost, st));
+  FSB_CUDA(cudaStreamSynchronize(st));
+  if (h) return fsb_set_error(FSB_ENCCL, "peer all-gather: a rank did not arrive (timeout)");
+  return FSB_OK;
+}

@@ -34,6 +34,7 @@ struct fsb_matrix {
   // so that the slice of x a wave of CTAs gathers from stays L2-resident -- cbcsr.h's column blocking applied to A'
   fsb_matrix* Tb = nullptr;
   int tb_blocks = 0;
+  size_t x_live_bytes = 0;    // != 0: bytes of the dense operand live at a time (one x block), for kernel-build choices
   // lazily built CSR view of a blocked / column-blocked matrix (same entries, stable by row, so
   // every row keeps its stored order); products default to the CSR kernels through it
   fsb_matrix* view = nullptr;
@@ -177,3 +178,10 @@ int fsb_comm_reduce_scatter_sum(const double* send, double* recv, size_t recvcou
 int fsb_comm_allgather(const double* send, double* recv, size_t sendcount, cudaStream_t st);
 int fsb_comm_group_start();
 int fsb_comm_group_end();
+// peer-memory (CUDA IPC over NVLink) symmetric buffer + all-gather by direct peer stores
+struct fsb_p2p;
+int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st);   // collective; error = keep using NCCL
+void fsb_p2p_destroy(fsb_p2p* p);
+void* fsb_p2p_local(fsb_p2p* p);
+int fsb_p2p_allgather_chunks(fsb_p2p* p, const double* loc, int C, long slice_doubles, cudaStream_t st);
+int fsb_p2p_check(fsb_p2p* p, cudaStream_t st);

@@ -453,6 +453,7 @@ int fsb_build_transpose_xblocked(fsb_matrix* A, size_t block_bytes, cudaStream_t
     delete T;
     return rc;
   }
+  T->x_live_bytes = (size_t)rpb * 8;
   A->Tb = T;
   A->tb_blocks = nb;
   return FSB_OK;

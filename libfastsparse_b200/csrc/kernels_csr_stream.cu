@@ -57,9 +57,8 @@ __global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restri
 // independent loads.  Two builds: 6 CTAs/SM (42 registers) is 11 % faster when the dense operand is small and mostly
 // hits in cache (C3 double SpMV, x = 8 MB: 0.97 vs 1.08 ms), 4 CTAs/SM (56 registers, all loads of a thread in flight)
 // is 13 % faster when it is large (the transpose, x = 80 MB: 1.31 vs 1.48 ms).  The launcher picks by operand size.
-// POL: L2 cache-policy words on the loads -- the matrix stream (cols / vals, touched once) is marked evict_first and
-// the gathered dense operand evict_last, so a 2.4 GB matrix stream cannot push an 80 MB x (the transposed product
-// of C3) out of the 126 MB L2; the staged kernel has used the same words since round 1 (fsb_device.cuh).
+// POL (knob "stream_policy", off by default): L2 cache-policy words on the loads -- the matrix stream (cols / vals,
+// touched once) evict_first, the gathered dense operand evict_last, like the staged kernel (fsb_device.cuh).
 template <int RT, bool VALS, int MINB, bool POL>
 __global__ void __launch_bounds__(kThreads, MINB)
 csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
@@ -213,8 +212,13 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
     FSB_KERNEL_CHECK();
     A->split_tile = kTile;
   }
-  const bool small_x = (double)A->ncol * RT * 8.0 <= 32e6;
-  const bool pol = fsb_knob("stream_policy", 1) != 0;
+  // bytes of the dense operand a wave of CTAs gathers from: the whole operand, or one block of it for an x-blocked transpose
+  const double x_live = A->x_live_bytes > 0 ? (double)A->x_live_bytes : (double)A->ncol * RT * 8.0;
+  const bool small_x = x_live <= 34e6;
+  // L2 policy words on the loads: measured neutral to slightly negative (C3 SpMV 0.965 -> 1.000 ms, transposed SpMV
+  // 1.318 -> 1.320 ms, DRAM bytes unchanged: profiles/r2a_ncu_spmv_policy.md) -- an operand that does not fit the
+  // ~60 MB a gather operand gets of B200's L2 is not kept by a hint; the x-blocked transpose fixes that case instead
+  const bool pol = fsb_knob("stream_policy", 0) != 0;
 #define FSB_STREAM_LAUNCH(MINB_, POL_)                                                                               \
   csr_stream_kernel<RT, VALS, MINB_, POL_><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, \
                                                                         A->split, carry_row, carry_val)
