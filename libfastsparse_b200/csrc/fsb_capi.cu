@@ -611,7 +611,7 @@ int fsb_spmm_host(fsb_matrix_t A, double* Y, const double* X, int R) {
   if (!A || !Y || !X || R <= 0) return fsb_set_error(FSB_EINVAL, "fsb_spmm_host: bad argument");
   std::lock_guard<std::mutex> lk(g_stage_mu);
   const size_t bx = (size_t)A->ncol * R * 8, by = (size_t)A->nrow * R * 8;
-  if (A->sharded && fsb_comm_active() && bx >= ((size_t)1 << 20)) {
+  if (A->sharded && fsb_comm_active() && bx >= ((size_t)1 << 20) && fsb_knob("host_x_allgather", FSB_MULTI_GPU_DEFAULTS)) {
     // row shard of a multi-GPU product: X is the same on every rank's host, so each rank sends only its 1/G of it over
     // PCIe and the rest arrives over NVLink (in-place all-gather) -- per-rank H2D drops from |X| to |X| / G
     const int G = fsb_comm_size(), rk = fsb_comm_rank();

@@ -162,6 +162,12 @@ struct CgShardWork {
   double *Pfull = nullptr, *KPpart = nullptr, *Xl = nullptr, *Rl = nullptr, *Pl = nullptr, *KPl = nullptr, *tmp = nullptr;
   double* Psend = nullptr;          // column halves of P_loc, the send buffers of the split all-gather
   fsb_p2p* p2p = nullptr;           // Pfull lives in a peer-mapped buffer: P is all-gathered by direct NVLink stores
+  // one iteration captured as a CUDA graph, one executable per parity of the G1 / G2 swap; valid for (gthr, glambda, gT)
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  double gthr = -1.0, glambda = 0.0;
+  const void* gT = nullptr;
+  const double* G1_first = nullptr; // the buffer that was G1 when the workspace was made: parity 0 <=> G1 == G1_first
+  void drop_graphs() { for (auto& g : gexec) { if (g) cudaGraphExecDestroy(g); g = nullptr; } }
   double *G1 = nullptr, *G2 = nullptr, *PtKP = nullptr, *Alpha = nullptr, *Psi = nullptr, *norm = nullptr, *inorm = nullptr;
   double *partial = nullptr;
   int *status = nullptr, *h_status = nullptr;
@@ -170,6 +176,7 @@ struct CgShardWork {
   cudaEvent_t ev_done = nullptr, ev_p = nullptr, ev_lo = nullptr, ev_hi = nullptr;
   void release() {
     cudaFree(Psend);
+    drop_graphs();
     for (cudaEvent_t e : {ev_p, ev_lo, ev_hi}) if (e) cudaEventDestroy(e);
     if (p2p) { fsb_p2p_destroy(p2p); p2p = nullptr; Pfull = nullptr; }
     cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
@@ -200,13 +207,14 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   shard_layout(F, R, w.G, &w.C, &w.s, &w.Fc, &w.Fp, &w.nloc);
   const size_t full = (size_t)w.Fp * R * 8, loc = (size_t)w.nloc * R * 8, rr = (size_t)R * R * 8;
   // Pfull in peer-mapped memory when CUDA IPC works between the ranks (knob "cg_p2p", default on); plain memory + NCCL otherwise
-  if (fsb_knob("cg_p2p", 1) && w.G > 1 && fsb_p2p_create(&w.p2p, full, fsb_default_stream()) == FSB_OK) w.Pfull = (double*)fsb_p2p_local(w.p2p);
+  if (fsb_knob("cg_p2p", FSB_MULTI_GPU_DEFAULTS) && w.G > 1 && fsb_p2p_create(&w.p2p, full, fsb_default_stream()) == FSB_OK) w.Pfull = (double*)fsb_p2p_local(w.p2p);
   else { w.p2p = nullptr; FSB_CUDA(cudaMalloc(&w.Pfull, full)); }
   FSB_CUDA(cudaMalloc(&w.KPpart, full));
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
   FSB_CUDA(cudaMalloc(&w.Psend, loc));
   FSB_CUDA(cudaMalloc(&w.tmp, std::max<size_t>((size_t)Nloc * R, 1) * 8));
   FSB_CUDA(cudaMalloc(&w.G1, rr)); FSB_CUDA(cudaMalloc(&w.G2, rr)); FSB_CUDA(cudaMalloc(&w.PtKP, rr));
+  w.G1_first = w.G1;
   FSB_CUDA(cudaMalloc(&w.Alpha, rr)); FSB_CUDA(cudaMalloc(&w.Psi, rr));
   FSB_CUDA(cudaMalloc(&w.norm, R * 8)); FSB_CUDA(cudaMalloc(&w.inorm, R * 8));
   FSB_CUDA(cudaMalloc(&w.partial, fsb_dense_gram_scratch_bytes(R)));
@@ -229,10 +237,16 @@ int csr_face(fsb_matrix* M, cudaStream_t st, fsb_matrix** out) {
   return FSB_OK;
 }
 
+// sum-allreduce of an R x R matrix: one peer-memory kernel when the ranks share mapped buffers, NCCL otherwise
+int shard_allreduce_small(CgShardWork& w, double* G, int n, cudaStream_t st) {
+  if (w.p2p && n <= 1024 && fsb_knob("cg_p2p_gram", 1)) return fsb_p2p_allreduce_small(w.p2p, G, n, st);
+  return fsb_allreduce_sum_dev(G, (long)n, (void*)st);
+}
+
 // G (R x R) = sum over ranks of Xa_loc' Xb_loc
 int shard_gram(CgShardWork& w, double* G, const double* Xa, const double* Xb, int R, cudaStream_t st) {
   FSB_TRY(fsb_dense_gram_into(G, w.partial, Xa, Xb, w.nloc, R, st));
-  return fsb_allreduce_sum_dev(G, (long)R * R, (void*)st);
+  return shard_allreduce_small(w, G, R * R, st);
 }
 
 // all-gather the local slices of every chunk of a sharded vector into the replicated layout
@@ -344,21 +358,19 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   if (cg_trace_level() >= 2)
     for (auto& e : pe) cudaEventCreate(&e);
   if (cg_trace()) { cudaStreamSynchronize(st); t_prev = now_ms(); }
-  while (queued < max_iter) {
-    const int nb = std::min(batch, max_iter - queued);
-    for (int k = 0; k < nb; ++k) {
-      const bool ph = cg_trace_level() >= 2 && k == 0;      // FSB_CG_TRACE=2: device time of the phases of an iteration
+  // one iteration, enqueued on st (and comm_st) without looking at the device; ph: FSB_CG_TRACE=2 phase events
+  auto enqueue_iteration = [&](double* g1, double* g2, bool ph) -> int {
       if (ph) cudaEventRecord(pe[0], st);
       FSB_TRY(shard_apply_op(A, Acsr, T, w, R, lambda, st, halves, ph ? pe + 6 : nullptr));
       if (ph) cudaEventRecord(pe[1], st);
       FSB_TRY(shard_gram(w, w.PtKP, w.Pl, w.KPl, R, st));
-      FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, w.G1, nullptr, 0, nullptr, 0, R, w.status, 0, 0.0, st));
+      FSB_TRY(fsb_dense_small_solve(w.Alpha, w.PtKP, g1, nullptr, 0, nullptr, 0, R, w.status, 0, 0.0, st));
       if (ph) cudaEventRecord(pe[2], st);
       FSB_TRY(fsb_dense_mix_add(w.Xl, w.Pl, w.Alpha, w.nloc, R, w.status, st));
       FSB_TRY(fsb_dense_mix_sub_gram(w.Rl, w.KPl, w.Alpha, w.partial, w.nloc, R, w.status, st, &np));
-      FSB_TRY(fsb_dense_gram_finalize(w.G2, w.partial, np, R, st));
-      FSB_TRY(fsb_allreduce_sum_dev(w.G2, (long)R * R, (void*)st));
-      FSB_TRY(fsb_dense_small_solve(w.Psi, w.G1, w.G2, nullptr, 0, nullptr, 0, R, w.status, 1, thr, st));
+      FSB_TRY(fsb_dense_gram_finalize(g2, w.partial, np, R, st));
+      FSB_TRY(shard_allreduce_small(w, g2, R * R, st));
+      FSB_TRY(fsb_dense_small_solve(w.Psi, g1, g2, nullptr, 0, nullptr, 0, R, w.status, 1, thr, st));
       if (ph) cudaEventRecord(pe[3], st);
       FSB_TRY(fsb_dense_mix_set(w.Pl, w.Pl, w.Rl, w.Psi, w.nloc, R, w.status, st));
       if (ph) cudaEventRecord(pe[4], st);
@@ -374,6 +386,47 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
       }
       halves = want_halves;
       if (ph) cudaEventRecord(pe[5], st);
+      return FSB_OK;
+  };
+  // CUDA graph of the iteration (knob "cg_graph", default on): an 8-GPU iteration is ~2 ms of ~35 dependent launches
+  // (kernels on two streams, NCCL, peer stores) and the host looks at the status words after every iteration -- enqueueing
+  // them one by one leaves the GPU idle for the launch latencies.  The iteration is captured once per parity of the
+  // G1 / G2 swap (after the first two iterations have run directly: they allocate scratch and time the products'
+  // launch candidates) and replayed with one cudaGraphLaunch.  Falls back to direct enqueueing if capture is refused.
+  const bool graph_ok = fsb_knob("cg_graph", FSB_MULTI_GPU_DEFAULTS) && cg_trace_level() < 2 && g_cg_dist_mode != 3;
+  if (w.gthr != thr || w.glambda != lambda || w.gT != (const void*)T) { w.drop_graphs(); w.gthr = thr; w.glambda = lambda; w.gT = (const void*)T; }
+  int direct_left = 2;     // iterations of this solve still to run uncaptured (only when no graph exists yet)
+  bool graph_broken = false;
+  while (queued < max_iter) {
+    const int nb = std::min(batch, max_iter - queued);
+    for (int k = 0; k < nb; ++k) {
+      const bool ph = cg_trace_level() >= 2 && k == 0;      // FSB_CG_TRACE=2: device time of the phases of an iteration
+      bool launched = false;
+      const int parity = w.G1 == w.G1_first ? 0 : 1;
+      if (graph_ok && !graph_broken && (w.gexec[parity] || direct_left <= 0)) {
+        if (!w.gexec[parity]) {
+          cudaGraph_t graph = nullptr;
+          cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+          int rc = ce == cudaSuccess ? enqueue_iteration(w.G1, w.G2, false) : FSB_ECUDA;
+          if (ce == cudaSuccess) ce = cudaStreamEndCapture(st, &graph);
+          if (ce == cudaSuccess && rc == FSB_OK) ce = cudaGraphInstantiate(&w.gexec[parity], graph, 0);
+          if (graph) cudaGraphDestroy(graph);
+          if (ce != cudaSuccess || rc != FSB_OK) {
+            cudaGetLastError();
+            w.gexec[parity] = nullptr;
+            graph_broken = true;
+            if (cg_trace()) fprintf(stderr, "[fsb cg %d/%d] graph capture refused (%s): enqueueing directly\n", w.rank, w.G, cudaGetErrorString(ce));
+          }
+        }
+        if (w.gexec[parity]) {
+          FSB_CUDA(cudaGraphLaunch(w.gexec[parity], st));
+          launched = true;
+        }
+      }
+      if (!launched) {
+        FSB_TRY(enqueue_iteration(w.G1, w.G2, ph));
+        --direct_left;
+      }
       std::swap(w.G1, w.G2);
     }
     queued += nb;

@@ -202,8 +202,11 @@ struct PushArgs {
 };
 
 // src: this rank's local slices [C][slice2] (double2 units); destination offset of slice (c, rank): c*chunk2 + rank*slice2
+// The epoch lives on the device (epoch_ptr, this rank's): the kernel publishes *epoch_ptr + 1 and stores it back, so the
+// same launch can be replayed from a CUDA graph (the block-CG iteration is captured once and replayed).
 __global__ void __launch_bounds__(256) p2p_push_kernel(const double2* __restrict__ src, PushArgs a, long long slice2, long long chunk2, int C,
-                                                       int G, int rank, unsigned long long epoch, unsigned int* __restrict__ counter) {
+                                                       int G, int rank, unsigned long long* __restrict__ epoch_ptr, unsigned int* __restrict__ counter) {
+  const unsigned long long epoch = *epoch_ptr + 1;     // every CTA reads it before any CTA can be "last"
   const int g = blockIdx.y;
   double2* __restrict__ dst = a.dst[g];
   const long long n = (long long)C * slice2;
@@ -223,19 +226,59 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(const double2* __restrict
   if (last) {
     __threadfence_system();
     if (threadIdx.x < G) st_release_sys(a.flags[threadIdx.x] + rank, epoch);
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x == 0) { *counter = 0; *epoch_ptr = epoch; }
   }
 }
 
 // one warp: lane g waits for rank g's flag; err[0] is set when a peer never shows up
-__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int G, unsigned long long epoch, int* __restrict__ err) {
+__global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, int G, const unsigned long long* __restrict__ epoch_ptr,
+                                int* __restrict__ err) {
   const int g = threadIdx.x;
   if (g >= G) return;
+  const unsigned long long epoch = *epoch_ptr;         // already advanced by this rank's push kernel (stream order)
   const long long t0 = clock64();
   while (ld_acquire_sys(flags + g) < epoch) {
     if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }    // ~4 s at 2 GHz
     __nanosleep(64);
   }
+}
+
+// Small sum-allreduce (the R x R Gram matrices of the block CG, <= kSmallMax doubles) in ONE single-CTA kernel: store
+// my vector into slot [parity][rank] of every rank, publish the epoch, wait for the G epochs, add the G slots in rank
+// order (identical bits on every rank -- the solver's ranks take identical branches without exchanging flags).
+// Two slot sets alternate by epoch parity: a rank can run at most one allreduce ahead of the slowest reader.
+constexpr int kSmallMax = 1024;
+struct SmallArgs {
+  double* slots[kMaxPeers];                 // every rank's slot area: [2][kMaxPeers][kSmallMax]
+  unsigned long long* flags[kMaxPeers];     // every rank's flag array for this channel: flags[g][src_rank]
+};
+__global__ void __launch_bounds__(256) p2p_small_allreduce_kernel(double* __restrict__ buf, int n, SmallArgs a, int G, int rank,
+                                                                  unsigned long long* __restrict__ epoch_ptr, int* __restrict__ err) {
+  const unsigned long long epoch = *epoch_ptr + 1;
+  const int par = (int)(epoch & 1);
+  for (int g = 0; g < G; ++g) {
+    double* dst = a.slots[g] + ((size_t)par * kMaxPeers + rank) * kSmallMax;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < G) {
+    st_release_sys(a.flags[threadIdx.x] + rank, epoch);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(a.flags[rank] + threadIdx.x) < epoch) {
+      if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  const double* mine = a.slots[rank] + (size_t)par * kMaxPeers * kSmallMax;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = mine[i];
+    for (int g = 1; g < G; ++g) s += mine[(size_t)g * kSmallMax + i];
+    buf[i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch_ptr = epoch;
 }
 
 }  // namespace
@@ -249,7 +292,11 @@ struct fsb_p2p {
   unsigned long long* peer_flags[kMaxPeers] = {};
   unsigned int* counter = nullptr;
   int* err = nullptr;
-  unsigned long long epoch = 0;
+  unsigned long long* epoch_dev = nullptr;  // epochs published so far (device-resident: graph-replayable)
+  // small-allreduce channel
+  double* slots = nullptr;
+  double* peer_slots[kMaxPeers] = {};
+  unsigned long long* epoch2_dev = nullptr;
 };
 
 namespace {
@@ -308,9 +355,14 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { cudaGetLastError(); rc = FSB_ECUDA; }
   void* pf[kMaxPeers] = {};
+  void* ps[kMaxPeers] = {};
+  void* slots = nullptr;
+  const size_t slot_bytes = (size_t)2 * kMaxPeers * kSmallMax * sizeof(double);
+  if (rc == FSB_OK && cudaMalloc(&slots, slot_bytes) != cudaSuccess) { cudaGetLastError(); rc = FSB_ECUDA; }
   int rc1 = rc == FSB_OK ? exchange_ipc(p->local, p->peer, st) : rc;
-  int rc2 = rc == FSB_OK ? exchange_ipc(flagpage, pf, st) : rc;     // both exchanges always run: they are collective
-  if (rc == FSB_OK) rc = rc1 != FSB_OK ? rc1 : rc2;
+  int rc2 = rc == FSB_OK ? exchange_ipc(flagpage, pf, st) : rc;     // the exchanges always run together: they are collective
+  int rc3 = rc == FSB_OK ? exchange_ipc(slots, ps, st) : rc;
+  if (rc == FSB_OK) rc = rc1 != FSB_OK ? rc1 : (rc2 != FSB_OK ? rc2 : rc3);
   // agree on the outcome
   double flag = rc == FSB_OK ? 0.0 : 1.0, *dflag = nullptr;
   if (cudaMalloc(&dflag, 8) == cudaSuccess) {
@@ -324,8 +376,9 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
     for (int g = 0; g < p->G; ++g) {
       if (g != p->rank && p->peer[g]) cudaIpcCloseMemHandle(p->peer[g]);
       if (g != p->rank && pf[g]) cudaIpcCloseMemHandle(pf[g]);
+      if (g != p->rank && ps[g]) cudaIpcCloseMemHandle(ps[g]);
     }
-    cudaFree(p->local); cudaFree(flagpage);
+    cudaFree(p->local); cudaFree(flagpage); cudaFree(slots);
     delete p;
     return rc != FSB_OK ? rc : fsb_set_error(FSB_ENCCL, "peer memory: another rank could not map the buffers");
   }
@@ -333,6 +386,10 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
   for (int g = 0; g < p->G; ++g) p->peer_flags[g] = (unsigned long long*)pf[g];
   p->counter = (unsigned int*)((char*)flagpage + 2048);
   p->err = (int*)((char*)flagpage + 2048 + 64);
+  p->epoch_dev = (unsigned long long*)((char*)flagpage + 2048 + 128);
+  p->epoch2_dev = (unsigned long long*)((char*)flagpage + 2048 + 192);
+  p->slots = (double*)slots;
+  for (int g = 0; g < p->G; ++g) p->peer_slots[g] = (double*)ps[g];
   *out = p;
   return FSB_OK;
 }
@@ -344,9 +401,11 @@ void fsb_p2p_destroy(fsb_p2p* p) {
     if (g == p->rank) continue;
     if (p->peer[g]) cudaIpcCloseMemHandle(p->peer[g]);
     if (p->peer_flags[g]) cudaIpcCloseMemHandle(p->peer_flags[g]);
+    if (p->peer_slots[g]) cudaIpcCloseMemHandle(p->peer_slots[g]);
   }
   cudaFree(p->local);
   cudaFree(p->flags);
+  cudaFree(p->slots);
   delete p;
 }
 
@@ -359,13 +418,26 @@ int fsb_p2p_allgather_chunks(fsb_p2p* p, const double* loc, int C, long slice, c
   if ((size_t)C * p->G * slice * 8 > p->bytes) return fsb_set_error(FSB_EINVAL, "peer all-gather: buffer too small");
   PushArgs a;
   for (int g = 0; g < kMaxPeers; ++g) { a.dst[g] = g < p->G ? (double2*)p->peer[g] : nullptr; a.flags[g] = g < p->G ? p->peer_flags[g] : nullptr; }
-  const unsigned long long epoch = ++p->epoch;
   const long long n2 = (long long)C * slice / 2;
   const int bx = (int)std::max<long long>(1, std::min<long long>((n2 + 255) / 256, (148 * 4) / p->G + 1));
   dim3 grid(bx, p->G);
-  p2p_push_kernel<<<grid, 256, 0, st>>>((const double2*)loc, a, slice / 2, (long long)p->G * slice / 2, C, p->G, p->rank, epoch, p->counter);
+  p2p_push_kernel<<<grid, 256, 0, st>>>((const double2*)loc, a, slice / 2, (long long)p->G * slice / 2, C, p->G, p->rank, p->epoch_dev, p->counter);
   FSB_KERNEL_CHECK();
-  p2p_wait_kernel<<<1, 32, 0, st>>>(p->flags, p->G, epoch, p->err);
+  p2p_wait_kernel<<<1, 32, 0, st>>>(p->flags, p->G, p->epoch_dev, p->err);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+// in-place sum-allreduce of n <= 1024 doubles over the peer-mapped slots (one kernel, ~10 us); identical bits on every rank
+int fsb_p2p_allreduce_small(fsb_p2p* p, double* buf, int n, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  if (n > kSmallMax) return fsb_set_error(FSB_EINVAL, "peer allreduce: at most %d doubles", kSmallMax);
+  SmallArgs a;
+  for (int g = 0; g < kMaxPeers; ++g) {
+    a.slots[g] = g < p->G ? p->peer_slots[g] : nullptr;
+    a.flags[g] = g < p->G ? p->peer_flags[g] + 64 : nullptr;     // second flag channel: words 64.. of the flag page
+  }
+  p2p_small_allreduce_kernel<<<1, 256, 0, st>>>(buf, n, a, p->G, p->rank, p->epoch2_dev, p->err);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }

@@ -63,6 +63,12 @@ struct fsb_matrix {
   void (*cg_cache_free)(void*) = nullptr;
 };
 
+// default of the multi-GPU fast paths (peer-store all-gather, peer Gram allreduce, CUDA-graph CG iteration, sharded
+// upload of X): switched on once verified on real multi-GPU hardware; the knobs cg_p2p / cg_graph / host_x_allgather override
+#ifndef FSB_MULTI_GPU_DEFAULTS
+#define FSB_MULTI_GPU_DEFAULTS 0
+#endif
+
 // ---- error plumbing (fsb_runtime.cu)
 int fsb_set_error(int code, const char* fmt, ...);
 int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line);
@@ -184,4 +190,5 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st);   // collectiv
 void fsb_p2p_destroy(fsb_p2p* p);
 void* fsb_p2p_local(fsb_p2p* p);
 int fsb_p2p_allgather_chunks(fsb_p2p* p, const double* loc, int C, long slice_doubles, cudaStream_t st);
+int fsb_p2p_allreduce_small(fsb_p2p* p, double* buf, int n, cudaStream_t st);   // n <= 1024, in place
 int fsb_p2p_check(fsb_p2p* p, cudaStream_t st);

@@ -44,11 +44,18 @@ constexpr int kLongRow = 2048;   // rows at least this long are split across the
 // 5.25 (lean) vs 5.10 ms (deep); power-law columns (C4) 2.98 (lean) vs 3.21 ms (deep): hot X rows
 // hit in L1/L2 and occupancy wins over depth there.  Neither saturates a unit (DRAM 62-81 %,
 // L2 51 %): the product sits on the random-gather throughput of L2 + HBM.
+// Round 2: the gather probe (profiles/r2_gather_ceiling.md) runs fastest with FEWER loads in flight per lane and more
+// resident warps once the operand misses L2; same-box sweep of the deep build (profiles/r2f_sweep_*): U=8 / 4 CTAs per SM
+// (54 registers) 4.86 ms at C2 and 3.17 ms at C4, U=6 / 5 CTAs (46 registers) 4.73 and 3.02 ms, U=4 / 6 CTAs 4.94 and
+// 2.99 ms, U=4 / 8 CTAs 4.84 and 3.54 ms.  Binary matrices take U=6 / 5; matrices with values keep U=8 / 4.
 #ifndef FSB_STAGED_U
-#define FSB_STAGED_U 8   // gathers per batch and lane
+#define FSB_STAGED_U 6        // gathers per batch and lane, binary matrices
+#endif
+#ifndef FSB_STAGED_U_VALS
+#define FSB_STAGED_U_VALS 8   // same, matrices with values
 #endif
 #ifndef FSB_STAGED_DEEP_MINB
-#define FSB_STAGED_DEEP_MINB 4
+#define FSB_STAGED_DEEP_MINB 5
 #endif
 #ifndef FSB_STAGED_DEEP_MINB_VALS      // matrices with values carry U more doubles per batch
 #define FSB_STAGED_DEEP_MINB_VALS 4
@@ -83,7 +90,7 @@ template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
                                          double (&acc)[VEC], const double* __restrict__ xbase, int ldx, bool col_ok,
                                          unsigned long long xpol) {
-  constexpr int U = FSB_STAGED_U;
+  constexpr int U = VALS ? FSB_STAGED_U_VALS : FSB_STAGED_U;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
     double vv[U];

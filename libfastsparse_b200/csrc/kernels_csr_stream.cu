@@ -31,6 +31,10 @@ constexpr int kThreads = 256;
 #define FSB_STREAM_TILE 2048   // 1024 measured 10 % slower at C3 (1.21 vs 1.10 ms); 4096 exceeds the 48 KB of static shared memory
 #endif
 template <int RT> struct Tile { static constexpr int n = FSB_STREAM_TILE / RT; };
+// lanes per row in the shared-memory row reduction when rows are short (<= 24 entries on average)
+#ifndef FSB_STREAM_SHORT_GL
+#define FSB_STREAM_SHORT_GL 1
+#endif
 
 // merge-path split: first i such that row_end[i] > d - i - 1, i.e. rows [0,i) are complete
 // once d items of the merged (row ends, entries) sequence are consumed
@@ -148,7 +152,7 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
       }
     }
   };
-  if (nn <= 24 * ndone) reduce_rows(std::integral_constant<int, 1>{});
+  if (nn <= 24 * ndone) reduce_rows(std::integral_constant<int, FSB_STREAM_SHORT_GL>{});
   else if (nn <= 128 * ndone) reduce_rows(std::integral_constant<int, 8>{});
   else reduce_rows(std::integral_constant<int, 32>{});
   // the row that continues past this tile: its piece here becomes a carry
