@@ -353,11 +353,12 @@ def run_ours(args):
         extras["shard_parity"] = {"row_slab_bit_identical_to_single_gpu_product": bool(flag.item())}
         del Yfull
     full_handle = full if world > 1 else None
-    if world == 1:
-        pass
     del Y
     if world > 1 and not args.no_collectives:
-        extras["collectives"] = collectives_block(args, fs, torch, dist, world, rank, full_handle, A, r0, r1, max_over_ranks, barrier)
+        try:
+            extras["collectives"] = collectives_block(args, fs, torch, dist, world, rank, full_handle, A, r0, r1, max_over_ranks, barrier)
+        except Exception as ex:      # deterministic failures hit every rank alike; the headline line must survive them
+            extras["collectives"] = {"error": f"{type(ex).__name__}: {ex}"[:500]}
     if full_handle is not None:
         full_handle.free()
 

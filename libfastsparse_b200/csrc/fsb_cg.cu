@@ -162,6 +162,7 @@ struct CgShardWork {
   double *Pfull = nullptr, *KPpart = nullptr, *Xl = nullptr, *Rl = nullptr, *Pl = nullptr, *KPl = nullptr, *tmp = nullptr;
   double* Psend = nullptr;          // column halves of P_loc, the send buffers of the split all-gather
   fsb_p2p* p2p = nullptr;           // Pfull lives in a peer-mapped buffer: P is all-gathered by direct NVLink stores
+  fsb_p2p* p2p_kp = nullptr;        // KPpart in a peer-mapped buffer: the reduce-scatter is a pull + ordered sum (knob cg_p2p_rs)
   // one iteration captured as a CUDA graph, one executable per parity of the G1 / G2 swap; valid for (gthr, glambda, gT)
   cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   double gthr = -1.0, glambda = 0.0;
@@ -179,6 +180,7 @@ struct CgShardWork {
     drop_graphs();
     for (cudaEvent_t e : {ev_p, ev_lo, ev_hi}) if (e) cudaEventDestroy(e);
     if (p2p) { fsb_p2p_destroy(p2p); p2p = nullptr; Pfull = nullptr; }
+    if (p2p_kp) { fsb_p2p_destroy(p2p_kp); p2p_kp = nullptr; KPpart = nullptr; }
     cudaFree(Pfull); cudaFree(KPpart); cudaFree(Xl); cudaFree(Rl); cudaFree(Pl); cudaFree(KPl); cudaFree(tmp);
     cudaFree(G1); cudaFree(G2); cudaFree(PtKP); cudaFree(Alpha); cudaFree(Psi); cudaFree(norm); cudaFree(inorm); cudaFree(partial);
     cudaFree(status);
@@ -209,7 +211,9 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   // Pfull in peer-mapped memory when CUDA IPC works between the ranks (knob "cg_p2p", default on); plain memory + NCCL otherwise
   if (fsb_knob("cg_p2p", FSB_MULTI_GPU_DEFAULTS) && w.G > 1 && fsb_p2p_create(&w.p2p, full, fsb_default_stream()) == FSB_OK) w.Pfull = (double*)fsb_p2p_local(w.p2p);
   else { w.p2p = nullptr; FSB_CUDA(cudaMalloc(&w.Pfull, full)); }
-  FSB_CUDA(cudaMalloc(&w.KPpart, full));
+  if (w.p2p && w.C <= 8 && fsb_knob("cg_p2p_rs", FSB_MULTI_GPU_DEFAULTS) && fsb_p2p_create(&w.p2p_kp, full, fsb_default_stream()) == FSB_OK)
+    w.KPpart = (double*)fsb_p2p_local(w.p2p_kp);
+  else { w.p2p_kp = nullptr; FSB_CUDA(cudaMalloc(&w.KPpart, full)); }
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));
   FSB_CUDA(cudaMalloc(&w.Psend, loc));
   FSB_CUDA(cudaMalloc(&w.tmp, std::max<size_t>((size_t)Nloc * R, 1) * 8));
@@ -302,14 +306,20 @@ int shard_apply_op(fsb_matrix* A, fsb_matrix* Acsr, fsb_matrix* T, CgShardWork& 
         FSB_TRY(fsb_launch_csr_spmm(&part, w.KPpart + (size_t)r0 * R, w.tmp, R, st));
       }
     }
+    if (w.p2p_kp) FSB_TRY(fsb_p2p_signal(w.p2p_kp, c, st));      // chunk c of my partial is complete: tell every rank
     FSB_CUDA(cudaEventRecord(w.ev[c], st));
     FSB_CUDA(cudaStreamWaitEvent(w.comm_st, w.ev[c], 0));
-    FSB_TRY(fsb_comm_reduce_scatter_sum(w.KPpart + (size_t)c * w.Fc * R, w.KPl + (size_t)c * w.s * R, (size_t)w.s * R, w.comm_st));
+    if (w.p2p_kp) {   // pull the G partial slices of my slice of chunk c over NVLink, add in rank order, + lambda P fused
+      FSB_TRY(fsb_p2p_pull_sum(w.p2p_kp, c, w.KPl + (size_t)c * w.s * R, (size_t)c * w.Fc * R + (size_t)w.rank * w.s * R, w.s * R,
+                               lambda != 0.0 ? w.Pl + (size_t)c * w.s * R : nullptr, lambda, w.comm_st));
+    } else {
+      FSB_TRY(fsb_comm_reduce_scatter_sum(w.KPpart + (size_t)c * w.Fc * R, w.KPl + (size_t)c * w.s * R, (size_t)w.s * R, w.comm_st));
+    }
   }
   if (trace) cudaEventRecord(trace[1], st);
   FSB_CUDA(cudaEventRecord(w.ev_done, w.comm_st));
   FSB_CUDA(cudaStreamWaitEvent(st, w.ev_done, 0));
-  if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(w.KPl, w.Pl, lambda, w.nloc * R, st));
+  if (lambda != 0.0 && !w.p2p_kp) FSB_TRY(fsb_dense_axpy_lambda(w.KPl, w.Pl, lambda, w.nloc * R, st));
   return FSB_OK;
 }
 
@@ -453,6 +463,7 @@ int cg_run_sharded(fsb_matrix* A, fsb_matrix* At, double* dX, const double* dB, 
   const int it = w.h_status[2];
   for (auto& e : pe) if (e) cudaEventDestroy(e);
   if (w.p2p) FSB_TRY(fsb_p2p_check(w.p2p, st));
+  if (w.p2p_kp) FSB_TRY(fsb_p2p_check(w.p2p_kp, st));
   // X = X_loc diag(norm), gathered into the replicated result (through the partial buffer: padded rows)
   for (int c = 0; c < w.C; ++c) FSB_TRY(fsb_dense_scale_cols(w.Xl + (size_t)c * w.s * R, w.norm, w.s, R, st));
   FSB_TRY(shard_allgather(w, w.KPpart, w.Xl, R, st));

@@ -281,6 +281,44 @@ __global__ void __launch_bounds__(256) p2p_small_allreduce_kernel(double* __rest
   if (threadIdx.x == 0) *epoch_ptr = epoch;
 }
 
+// Reduce-scatter by PULL: after a rank has produced chunk c of its full-length partial it signals the chunk's epoch to
+// every peer; the owner of a slice then reads the G partial slices straight out of the peers' buffers (NVLink loads)
+// and adds them in rank order, plus lambda * add[] (the "+ lambda P" of the CG operator).
+__global__ void p2p_signal_kernel(SmallArgs a, int G, int rank, int word0, unsigned long long* __restrict__ epoch_ptr) {
+  const unsigned long long epoch = *epoch_ptr + 1;
+  __syncwarp();
+  if (threadIdx.x < G) st_release_sys(a.flags[threadIdx.x] + word0 + rank, epoch);
+  __syncwarp();
+  if (threadIdx.x == 0) *epoch_ptr = epoch;
+}
+
+struct PullArgs { const double2* src[kMaxPeers]; };
+__global__ void __launch_bounds__(256) p2p_pull_sum_kernel(double2* __restrict__ out, PullArgs a, long long n2, int G,
+                                                           const unsigned long long* __restrict__ flags, const unsigned long long* __restrict__ epoch_ptr,
+                                                           const double2* __restrict__ add, double lambda, int* __restrict__ err) {
+  if (threadIdx.x < G) {
+    const unsigned long long epoch = *epoch_ptr;       // this rank's own signal count for the chunk (already advanced)
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+      if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    double2 v[kMaxPeers];
+#pragma unroll
+    for (int g = 0; g < kMaxPeers; ++g)
+      if (g < G) v[g] = a.src[g][i];
+    double2 s = v[0];
+#pragma unroll
+    for (int g = 1; g < kMaxPeers; ++g)
+      if (g < G) { s.x += v[g].x; s.y += v[g].y; }
+    if (add) { const double2 p = add[i]; s.x = fma(lambda, p.x, s.x); s.y = fma(lambda, p.y, s.y); }
+    out[i] = s;
+  }
+}
+
 }  // namespace
 
 struct fsb_p2p {
@@ -297,6 +335,7 @@ struct fsb_p2p {
   double* slots = nullptr;
   double* peer_slots[kMaxPeers] = {};
   unsigned long long* epoch2_dev = nullptr;
+  unsigned long long* epoch3_dev = nullptr;   // [8]: per-channel signal counts (reduce-scatter by pull)
 };
 
 namespace {
@@ -388,6 +427,7 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
   p->err = (int*)((char*)flagpage + 2048 + 64);
   p->epoch_dev = (unsigned long long*)((char*)flagpage + 2048 + 128);
   p->epoch2_dev = (unsigned long long*)((char*)flagpage + 2048 + 192);
+  p->epoch3_dev = (unsigned long long*)((char*)flagpage + 2048 + 256);
   p->slots = (double*)slots;
   for (int g = 0; g < p->G; ++g) p->peer_slots[g] = (double*)ps[g];
   *out = p;
@@ -438,6 +478,33 @@ int fsb_p2p_allreduce_small(fsb_p2p* p, double* buf, int n, cudaStream_t st) {
     a.flags[g] = g < p->G ? p->peer_flags[g] + 64 : nullptr;     // second flag channel: words 64.. of the flag page
   }
   p2p_small_allreduce_kernel<<<1, 256, 0, st>>>(buf, n, a, p->G, p->rank, p->epoch2_dev, p->err);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+// "chunk `channel` of my buffer is complete": publish the channel's next epoch to every rank (channel < 8)
+int fsb_p2p_signal(fsb_p2p* p, int channel, cudaStream_t st) {
+  if (channel < 0 || channel >= 8) return fsb_set_error(FSB_EINVAL, "peer signal: channel out of range");
+  SmallArgs a;
+  for (int g = 0; g < kMaxPeers; ++g) { a.slots[g] = nullptr; a.flags[g] = g < p->G ? p->peer_flags[g] : nullptr; }
+  p2p_signal_kernel<<<1, 32, 0, st>>>(a, p->G, p->rank, 128 + channel * 8, p->epoch3_dev + channel);
+  FSB_KERNEL_CHECK();
+  return FSB_OK;
+}
+
+// out[0..n) = sum over ranks g (in rank order) of rank g's buffer[elem_offset .. +n)  (+ lambda * add[0..n) when add != nullptr),
+// after every rank has signalled `channel` as often as this rank has.  n even, offsets 16-byte aligned.
+int fsb_p2p_pull_sum(fsb_p2p* p, int channel, double* out, size_t elem_offset, long n, const double* add, double lambda, cudaStream_t st) {
+  if (n <= 0) return FSB_OK;
+  if (n % 2 || elem_offset % 2 || ((uintptr_t)out & 15) || (add && ((uintptr_t)add & 15)))
+    return fsb_set_error(FSB_EINVAL, "peer reduce-scatter: operands must be 16-byte aligned");
+  if ((elem_offset + (size_t)n) * 8 > p->bytes) return fsb_set_error(FSB_EINVAL, "peer reduce-scatter: range outside the buffer");
+  PullArgs a;
+  for (int g = 0; g < kMaxPeers; ++g) a.src[g] = g < p->G ? (const double2*)((const double*)p->peer[g] + elem_offset) : nullptr;
+  const long long n2 = n / 2;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n2 + 255) / 256, 128));
+  p2p_pull_sum_kernel<<<grid, 256, 0, st>>>((double2*)out, a, n2, p->G, p->flags + 128 + channel * 8, p->epoch3_dev + channel, (const double2*)add,
+                                             lambda, p->err);
   FSB_KERNEL_CHECK();
   return FSB_OK;
 }

@@ -191,4 +191,6 @@ void fsb_p2p_destroy(fsb_p2p* p);
 void* fsb_p2p_local(fsb_p2p* p);
 int fsb_p2p_allgather_chunks(fsb_p2p* p, const double* loc, int C, long slice_doubles, cudaStream_t st);
 int fsb_p2p_allreduce_small(fsb_p2p* p, double* buf, int n, cudaStream_t st);   // n <= 1024, in place
+int fsb_p2p_signal(fsb_p2p* p, int channel, cudaStream_t st);
+int fsb_p2p_pull_sum(fsb_p2p* p, int channel, double* out, size_t elem_offset, long n, const double* add, double lambda, cudaStream_t st);
 int fsb_p2p_check(fsb_p2p* p, cudaStream_t st);
