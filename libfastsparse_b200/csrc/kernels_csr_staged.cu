@@ -118,52 +118,6 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
   }
 }
 
-// Same walk with the staged indices fetched FOUR at a time (one 128-bit LDS per four entries instead of four 32-bit
-// ones).  ncu at C4 (profiles/r2a_ncu_c4.md): the LSU data pipe is the busiest unit (77 %) and 28 % of its wavefronts
-// are these shared-memory index reads (173 M of 625 M).  `sc` is the 16-byte aligned staging buffer, [s, e) the row's
-// positions in it; batches start at the aligned position below s, slots outside [s, e) are predicated off (the
-// buffer has 16 entries of slack past the staged run).  The order of the adds is unchanged (stored order).
-#ifndef FSB_STAGED_LDS128
-#define FSB_STAGED_LDS128 0
-#endif
-template <int G, int VEC, bool VALS, bool DEEP>
-__device__ __forceinline__ void walk_row_lds128(const int* __restrict__ sc, const double* __restrict__ vi, int voff, int s, int e,
-                                                double (&acc)[VEC], const double* __restrict__ xbase, int ldx, bool col_ok,
-                                                unsigned long long xpol) {
-  constexpr int U = 8;
-  for (int p = s & ~3; p < e; p += U) {
-    const int4 a = *reinterpret_cast<const int4*>(sc + p);
-    const int4 b = *reinterpret_cast<const int4*>(sc + p + 4);
-    const int c[U] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    double xr[U][VEC];
-    double vv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = p + u;
-      if (idx >= s && idx < e && col_ok) {
-        if (VALS) vv[u] = vi[idx - voff];
-        XLoad<VEC>::ldp(xr[u], xbase + (long long)c[u] * ldx, xpol);
-      } else {
-        if (VALS) vv[u] = 0.0;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) xr[u][v] = 0.0;
-      }
-    }
-    if (DEEP) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) pin_after_loads<VEC>(xr[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = p + u;
-      if (idx >= s && idx < e) {     // skipped slots must not touch acc: -0.0 + 0.0 would flip the sign of an empty sum
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = VALS ? fma(xr[u][v], vv[u], acc[v]) : acc[v] + xr[u][v];
-      }
-    }
-  }
-}
-
 // optional fused epilogue: acc += lambda * Z[row, cols]  (the "+ lambda P" of the CG operator, cg.h:19-21)
 template <int VEC>
 __device__ __forceinline__ void add_scaled_row(double (&acc)[VEC], const double* __restrict__ Z, double lambda, long long off) {
@@ -236,14 +190,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-#if FSB_STAGED_LDS128
-      {
-        const int sh = (int)(ci - s_cols);      // 0..3: shift of the run inside the aligned staging buffer
-        walk_row_lds128<G, VEC, VALS, DEEP>(s_cols, vi, sh, s_rp[r] - base + sh, s_rp[r + 1] - base + sh, acc, xbase, ldx, col_ok, xpol);
-      }
-#else
       walk_row<G, VEC, VALS, true, DEEP>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol);
-#endif
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);

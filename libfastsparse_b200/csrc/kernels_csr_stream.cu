@@ -31,9 +31,10 @@ constexpr int kThreads = 256;
 #define FSB_STREAM_TILE 2048   // 1024 measured 10 % slower at C3 (1.21 vs 1.10 ms); 4096 exceeds the 48 KB of static shared memory
 #endif
 template <int RT> struct Tile { static constexpr int n = FSB_STREAM_TILE / RT; };
-// lanes per row in the shared-memory row reduction when rows are short (<= 24 entries on average)
+// lanes per row in the shared-memory row reduction when rows are short (<= 24 entries on average): C3 double SpMV
+// 0.966 ms with 1 lane, 0.949 with 2, 1.000 with 4 (profiles/r2g_c3_{base,sgl2,sgl4}.jsonl)
 #ifndef FSB_STREAM_SHORT_GL
-#define FSB_STREAM_SHORT_GL 1
+#define FSB_STREAM_SHORT_GL 2
 #endif
 
 // merge-path split: first i such that row_end[i] > d - i - 1, i.e. rows [0,i) are complete
