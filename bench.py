@@ -310,6 +310,7 @@ def run_ours(args):
     xp = C.cast(Xh.data_ptr(), C.POINTER(C.c_double)); yp = C.cast(Yh.data_ptr(), C.POINTER(C.c_double))
     if world > 1:
         A.set_row_sharded(True)      # sharded handle: every rank uploads 1/N of X, the rest arrives over NVLink (all-gather)
+        fs.check(L.fsb_tune(b"host_x_allgather", 1))
     fs.check(L.fsb_spmm_host(A.h, yp, xp, R))
     barrier()
     t0 = time.perf_counter()

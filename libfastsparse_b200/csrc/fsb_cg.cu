@@ -211,7 +211,7 @@ int shard_alloc(CgShardWork& w, long F, long Nloc, int R) {
   // Pfull in peer-mapped memory when CUDA IPC works between the ranks (knob "cg_p2p", default on); plain memory + NCCL otherwise
   if (fsb_knob("cg_p2p", FSB_MULTI_GPU_DEFAULTS) && w.G > 1 && fsb_p2p_create(&w.p2p, full, fsb_default_stream()) == FSB_OK) w.Pfull = (double*)fsb_p2p_local(w.p2p);
   else { w.p2p = nullptr; FSB_CUDA(cudaMalloc(&w.Pfull, full)); }
-  if (w.p2p && w.C <= 8 && fsb_knob("cg_p2p_rs", FSB_MULTI_GPU_DEFAULTS) && fsb_p2p_create(&w.p2p_kp, full, fsb_default_stream()) == FSB_OK)
+  if (w.p2p && w.C <= 8 && fsb_knob("cg_p2p_rs", 0) && fsb_p2p_create(&w.p2p_kp, full, fsb_default_stream()) == FSB_OK)
     w.KPpart = (double*)fsb_p2p_local(w.p2p_kp);
   else { w.p2p_kp = nullptr; FSB_CUDA(cudaMalloc(&w.KPpart, full)); }
   FSB_CUDA(cudaMalloc(&w.Xl, loc)); FSB_CUDA(cudaMalloc(&w.Rl, loc)); FSB_CUDA(cudaMalloc(&w.Pl, loc)); FSB_CUDA(cudaMalloc(&w.KPl, loc));

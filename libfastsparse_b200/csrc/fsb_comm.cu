@@ -182,7 +182,7 @@ int fsb_partition_rows(int nrow, const int* row_ptr, int nparts, int* bounds) {
 //     intermediate protocol buffers: the bytes cross the switch once, at the rate the SMs can push them.
 // Safe reuse without double buffering: a rank can only reach its next push after the reduce-scatter of the current
 // iteration, which needs every rank's A'(A P) partial, i.e. every rank has finished reading the previous P.
-// The wait kernel gives up after ~4 s (a peer died) and raises a device-side error flag instead of hanging the GPU.
+// The wait kernel gives up after ~15 s (a peer died) and raises a device-side error flag instead of hanging the GPU.
 namespace {
 
 constexpr int kMaxPeers = 8;
@@ -238,7 +238,7 @@ __global__ void p2p_wait_kernel(const unsigned long long* __restrict__ flags, in
   const unsigned long long epoch = *epoch_ptr;         // already advanced by this rank's push kernel (stream order)
   const long long t0 = clock64();
   while (ld_acquire_sys(flags + g) < epoch) {
-    if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }    // ~4 s at 2 GHz
+    if (clock64() - t0 > 30000000000LL) { atomicExch(err, 1); break; }    // ~15 s at 2 GHz
     __nanosleep(64);
   }
 }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) p2p_small_allreduce_kernel(double* __rest
     st_release_sys(a.flags[threadIdx.x] + rank, epoch);
     const long long t0 = clock64();
     while (ld_acquire_sys(a.flags[rank] + threadIdx.x) < epoch) {
-      if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+      if (clock64() - t0 > 30000000000LL) { atomicExch(err, 1); break; }
       __nanosleep(32);
     }
   }
@@ -300,22 +300,34 @@ __global__ void __launch_bounds__(256) p2p_pull_sum_kernel(double2* __restrict__
     const unsigned long long epoch = *epoch_ptr;       // this rank's own signal count for the chunk (already advanced)
     const long long t0 = clock64();
     while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-      if (clock64() - t0 > 8000000000LL) { atomicExch(err, 1); break; }
+      if (clock64() - t0 > 30000000000LL) { atomicExch(err, 1); break; }
       __nanosleep(64);
     }
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-    double2 v[kMaxPeers];
+  // NVLink loads have a few microseconds of latency: keep kUnroll x G independent 16-byte loads in flight per thread
+  constexpr int kUnroll = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += stride * kUnroll) {
+    double2 v[kUnroll][kMaxPeers];
 #pragma unroll
-    for (int g = 0; g < kMaxPeers; ++g)
-      if (g < G) v[g] = a.src[g][i];
-    double2 s = v[0];
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
 #pragma unroll
-    for (int g = 1; g < kMaxPeers; ++g)
-      if (g < G) { s.x += v[g].x; s.y += v[g].y; }
-    if (add) { const double2 p = add[i]; s.x = fma(lambda, p.x, s.x); s.y = fma(lambda, p.y, s.y); }
-    out[i] = s;
+      for (int g = 0; g < kMaxPeers; ++g)
+        if (g < G && i < n2) v[u][g] = a.src[g][i];
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n2) break;
+      double2 s = v[u][0];
+#pragma unroll
+      for (int g = 1; g < kMaxPeers; ++g)
+        if (g < G) { s.x += v[u][g].x; s.y += v[u][g].y; }
+      if (add) { const double2 p = add[i]; s.x = fma(lambda, p.x, s.x); s.y = fma(lambda, p.y, s.y); }
+      out[i] = s;
+    }
   }
 }
 
@@ -502,7 +514,7 @@ int fsb_p2p_pull_sum(fsb_p2p* p, int channel, double* out, size_t elem_offset, l
   PullArgs a;
   for (int g = 0; g < kMaxPeers; ++g) a.src[g] = g < p->G ? (const double2*)((const double*)p->peer[g] + elem_offset) : nullptr;
   const long long n2 = n / 2;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((n2 + 255) / 256, 128));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n2 + 255) / 256, 148));   // 160 registers: one CTA per SM
   p2p_pull_sum_kernel<<<grid, 256, 0, st>>>((double2*)out, a, n2, p->G, p->flags + 128 + channel * 8, p->epoch3_dev + channel, (const double2*)add,
                                              lambda, p->err);
   FSB_KERNEL_CHECK();

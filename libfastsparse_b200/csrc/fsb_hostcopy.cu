@@ -61,7 +61,10 @@ int copy_threads() {
   if (n == 0) {
     const char* e = getenv("FSB_COPY_THREADS");
     int want = e ? atoi(e) : 8;
-    const int hw = (int)std::thread::hardware_concurrency();
+    int hw = (int)std::thread::hardware_concurrency();
+    // one process per GPU: the ranks of a node share its cores (8 ranks x 8 copy threads on 32 cores: 188 ms per
+    // product instead of 30, profiles/r2h_bench_c2_n8.json)
+    if (hw > 0 && fsb_comm_size() > 1) hw = std::max(2, hw / fsb_comm_size());
     if (hw > 0) want = std::min(want, hw);
     n = std::max(want, 1);
   }

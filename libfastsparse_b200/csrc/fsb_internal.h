@@ -63,10 +63,12 @@ struct fsb_matrix {
   void (*cg_cache_free)(void*) = nullptr;
 };
 
-// default of the multi-GPU fast paths (peer-store all-gather, peer Gram allreduce, CUDA-graph CG iteration, sharded
-// upload of X): switched on once verified on real multi-GPU hardware; the knobs cg_p2p / cg_graph / host_x_allgather override
+// default of the multi-GPU fast paths (peer-store all-gather of P, peer Gram allreduce, CUDA-graph CG iteration, sharded
+// upload of X): verified on 2 and 8 B200 (profiles/r2e_*, r2h_*: results identical to NCCL, all ranks bit-identical);
+// the knobs cg_p2p / cg_p2p_gram / cg_graph / host_x_allgather override.  The reduce-scatter by pull (cg_p2p_rs) stays
+// off: 2.385 against 2.351 ms per iteration on 8 GPUs -- its loads compete with the products it overlaps.
 #ifndef FSB_MULTI_GPU_DEFAULTS
-#define FSB_MULTI_GPU_DEFAULTS 0
+#define FSB_MULTI_GPU_DEFAULTS 1
 #endif
 
 // ---- error plumbing (fsb_runtime.cu)
