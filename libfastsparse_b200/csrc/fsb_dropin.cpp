@@ -379,8 +379,10 @@ int fsb_cache_settle(void) {
     }
     std::lock_guard<std::mutex> lk(g_mu);
     p.e->pins--;
-    if (p.job && now != p.e->full) {
-      ++stale;
+    const bool is_stale = p.job && now != p.e->full;
+    if (is_stale) ++stale;
+    const bool orphan = p.e->k0 == nullptr;        // dropped or found stale by another call while this one used it
+    if (is_stale || orphan) {
       for (size_t i = 0; i < g_entries.size(); ++i)
         if (g_entries[i] == p.e) {
           if (p.e->pins == 0) drop_entry_locked(i); else p.e->k0 = p.e->k1 = p.e->k2 = nullptr;
