@@ -351,10 +351,12 @@ struct fsb_p2p {
 };
 
 namespace {
-// every rank contributes one IPC handle; out[g] = rank g's allocation mapped into this process
+// every rank contributes one IPC handle; out[g] = rank g's allocation mapped into this process.  COLLECTIVE: a rank
+// whose own allocation failed still takes part (mine == nullptr is announced as "no handle"), so nobody hangs.
 int exchange_ipc(void* mine, void* out[kMaxPeers], cudaStream_t st) {
   cudaIpcMemHandle_t h;
-  int ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess ? 1 : 0;
+  memset(&h, 0, sizeof h);
+  int ok = (mine && cudaIpcGetMemHandle(&h, mine) == cudaSuccess) ? 1 : 0;
   if (!ok) cudaGetLastError();
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   constexpr int kWords = 16;                // 64 bytes of handle + status, in doubles
@@ -410,9 +412,10 @@ int fsb_p2p_create(fsb_p2p** out, size_t bytes, cudaStream_t st) {
   void* slots = nullptr;
   const size_t slot_bytes = (size_t)2 * kMaxPeers * kSmallMax * sizeof(double);
   if (rc == FSB_OK && cudaMalloc(&slots, slot_bytes) != cudaSuccess) { cudaGetLastError(); rc = FSB_ECUDA; }
-  int rc1 = rc == FSB_OK ? exchange_ipc(p->local, p->peer, st) : rc;
-  int rc2 = rc == FSB_OK ? exchange_ipc(flagpage, pf, st) : rc;     // the exchanges always run together: they are collective
-  int rc3 = rc == FSB_OK ? exchange_ipc(slots, ps, st) : rc;
+  // the three exchanges always run, whatever happened locally: they are collective
+  const int rc1 = exchange_ipc(rc == FSB_OK ? p->local : nullptr, p->peer, st);
+  const int rc2 = exchange_ipc(rc == FSB_OK ? flagpage : nullptr, pf, st);
+  const int rc3 = exchange_ipc(rc == FSB_OK ? slots : nullptr, ps, st);
   if (rc == FSB_OK) rc = rc1 != FSB_OK ? rc1 : (rc2 != FSB_OK ? rc2 : rc3);
   // agree on the outcome
   double flag = rc == FSB_OK ? 0.0 : 1.0, *dflag = nullptr;
