@@ -130,9 +130,7 @@ static inline void bsdm_A_mul_Bn(double* y, struct BlockedSDM* B, double* x, int
 /* per-block Hilbert order carrying the values (dsparse.h:193-216) */
 static inline void sort_bsdm(struct BlockedSDM* B) {
   fsb_cache_drop(B->start_row);
-  for (int b = 0; b < B->nblocks; b++)
-    if (fsb_host_sort_block_hilbert(B->start_row[b], B->start_row[b + 1] - B->start_row[b], B->nnz[b], B->rows[b], B->cols[b], B->vals[b]))
-      fsb_die("sort_bsdm");
+  if (fsb_sort_blocked_auto(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, B->vals, 1)) fsb_die("sort_bsdm");
 }
 
 #endif /* DSPARSE_H */

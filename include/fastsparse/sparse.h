@@ -153,16 +153,13 @@ static inline struct BlockedSBM* new_bsbm(struct SparseBinaryMatrix* A, int bloc
 /* per block: Hilbert order inside n x n tiles along the row strip (sparse.h:215-236) */
 static inline void sort_bsbm(struct BlockedSBM* B) {
   fsb_cache_drop(B->start_row);
-  for (int b = 0; b < B->nblocks; b++)
-    if (fsb_host_sort_block_hilbert(B->start_row[b], B->start_row[b + 1] - B->start_row[b], B->nnz[b], B->rows[b], B->cols[b], NULL))
-      fsb_die("sort_bsbm");
+  if (fsb_sort_blocked_auto(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, NULL, 1)) fsb_die("sort_bsbm");
 }
 
 /* per block: row-major order (sparse.h:238-256) */
 static inline void sort_bsbm_byrow(struct BlockedSBM* B) {
   fsb_cache_drop(B->start_row);
-  for (int b = 0; b < B->nblocks; b++)
-    if (fsb_host_sort_block_byrow(B->ncol, B->nnz[b], B->rows[b], B->cols[b])) fsb_die("sort_bsbm_byrow");
+  if (fsb_sort_blocked_auto(B->nrow, B->ncol, B->nblocks, B->start_row, B->nnz, B->rows, B->cols, NULL, 2)) fsb_die("sort_bsbm_byrow");
 }
 
 /* Y = B X with ncol right-hand sides, row-major operands (sparse.h:318-336) */

@@ -113,6 +113,13 @@ int fsb_sort_coo_hilbert_dev(int nrow, int ncol, long nnz, int* d_rows, int* d_c
 int fsb_sort_coo_hilbert(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals);
 /* the drop-in's choice: device sort at >= FSB_SORT_DEVICE_MIN entries when a device is present, else the host routine */
 int fsb_sort_coo_hilbert_auto(int nrow, int ncol, long nnz, int* rows, int* cols, double* vals);
+/* per-block orders of a HOST BlockedSBM / BlockedSDM on the device (upload, one keyed radix sort over all blocks, copy
+ * back): order 1 = sort_bsbm sparse.h:215-236 / sort_bsdm dsparse.h:193-216 (row_xy2d Hilbert key), order 2 =
+ * sort_bsbm_byrow sparse.h:238-256; vals == NULL for binary.  _auto: device at >= FSB_SORT_DEVICE_MIN entries, else host. */
+int fsb_sort_blocked(int nrow, int ncol, int nblocks, const int* start_row, const int* blk_nnz, int* const* rows,
+                     int* const* cols, double* const* vals, int order);
+int fsb_sort_blocked_auto(int nrow, int ncol, int nblocks, const int* start_row, const int* blk_nnz, int* const* rows,
+                          int* const* cols, double* const* vals, int order);
 /* column-blocked binary CSR built on the device (new_cbcsr cbcsr.h:16-65) */
 int fsb_cbcsr_from_coo_dev(fsb_matrix_t* out, int nrow, int ncol, long nnz, const int* d_rows,
                            const int* d_cols, int colblocksize);

@@ -40,6 +40,8 @@ _SIGS = {
     "fsb_cbcsr_from_coo_dev": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int]),
     "fsb_sort_coo_hilbert_dev": (C.c_int, [C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fsb_sort_coo_hilbert": (C.c_int, [C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
+    "fsb_sort_blocked": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp, C.c_int]),
+    "fsb_sort_blocked_auto": (C.c_int, [C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp, C.c_int]),
     "fsb_sort_coo_hilbert_auto": (C.c_int, [C.c_int, C.c_int, C.c_long, c_int_p, c_int_p, c_dbl_p]),
     "fsb_cbcsr_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, c_int_p, c_int_p]),
     "fsb_blocked_upload": (C.c_int, [C.POINTER(handle), C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_pp, c_int_pp, c_dbl_pp]),

@@ -320,17 +320,29 @@ def new_bsbm(A, block_size):                                  # sparse.h:175-213
     return _new_blocked(A, block_size, BlockedSBM)
 
 
-def sort_bsbm(B):                                             # sparse.h:215-236 / dsparse.h:193-216
+def _sort_blocked(B, order, device=None):
+    """device=None: the drop-in's choice (device at >= FSB_SORT_DEVICE_MIN entries when a GPU is present); True / False force it."""
     B._drop()
-    for b in range(B.nblocks):
-        check(lib().fsb_host_sort_block_hilbert(int(B.start_row[b]), int(B.start_row[b + 1] - B.start_row[b]), int(B.nnz[b]),
-                                                _ip(B.rows[b]), _ip(B.cols[b]), _dp(B.vals[b]) if B.vals is not None else None))
+    rp, cp = B._ptrs(B.rows, c_int_p), B._ptrs(B.cols, c_int_p)
+    vp = B._ptrs(B.vals, c_dbl_p) if B.vals is not None else None
+    if device is False:
+        for b in range(B.nblocks):
+            if order == 1:
+                check(lib().fsb_host_sort_block_hilbert(int(B.start_row[b]), int(B.start_row[b + 1] - B.start_row[b]), int(B.nnz[b]),
+                                                        _ip(B.rows[b]), _ip(B.cols[b]), _dp(B.vals[b]) if B.vals is not None else None))
+            else:
+                check(lib().fsb_host_sort_block_byrow(B.ncol, int(B.nnz[b]), _ip(B.rows[b]), _ip(B.cols[b])))
+        return
+    fn = lib().fsb_sort_blocked if device else lib().fsb_sort_blocked_auto
+    check(fn(B.nrow, B.ncol, B.nblocks, _ip(B.start_row), _ip(B.nnz), rp, cp, vp, order))
 
 
-def sort_bsbm_byrow(B):                                       # sparse.h:238-256
-    B._drop()
-    for b in range(B.nblocks):
-        check(lib().fsb_host_sort_block_byrow(B.ncol, int(B.nnz[b]), _ip(B.rows[b]), _ip(B.cols[b])))
+def sort_bsbm(B, device=None):                                # sparse.h:215-236 / dsparse.h:193-216
+    _sort_blocked(B, 1, device)
+
+
+def sort_bsbm_byrow(B, device=None):                          # sparse.h:238-256
+    _sort_blocked(B, 2, device)
 
 
 def bsbm_A_mul_Bn(y, B, x, ncol):                             # sparse.h:318-336

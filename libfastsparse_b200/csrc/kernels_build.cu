@@ -10,6 +10,8 @@
 //     (SURVEY 8d): entry j is a pure function of (seed, j).
 #include <stdlib.h>
 
+#include <vector>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "fsb_internal.h"
@@ -717,6 +719,134 @@ extern "C" int fsb_sort_coo_hilbert(int nrow, int ncol, long nnz, int* rows, int
   if (rc == FSB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "fsb_sort_coo_hilbert", __FILE__, __LINE__);
   cudaFree(dr); cudaFree(dc); cudaFree(dv);
   return rc;
+}
+
+// ---------------------------------------------------------------- per-block orders of a HOST blocked structure
+namespace {
+// key = (block << 40) | in-block key; order 1: row_xy2d(n_b, row - start_row[b], col) with n_b = ceilPower2(rows of block b)
+// (sort_bsbm sparse.h:215-236, hilbert.h:60-65), order 2: (row - start_row[b]) * ncol + col (sort_bsbm_byrow sparse.h:238-256)
+__global__ void host_blocked_sortkey_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long nnz,
+                                            const long* __restrict__ blk_off, const int* __restrict__ start_row, int nblocks, int ncol,
+                                            int order, unsigned long long* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < nnz; i += stride) {
+    int lo = 0, hi = nblocks;  // largest b with blk_off[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (blk_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int r0 = start_row[lo], lr = rows[i] - r0, c = cols[i];
+    unsigned long long low;
+    if (order == 1) {
+      const int n = dev_ceil_pow2(start_row[lo + 1] - r0);
+      low = (unsigned long long)(dev_xy2d(n, c % n, lr) + (long long)n * n * (c / n));
+    } else {
+      low = (unsigned long long)lr * (unsigned long long)ncol + (unsigned long long)c;
+    }
+    keys[i] = ((unsigned long long)lo << 40) | (low & ((1ull << 40) - 1));
+  }
+}
+}  // namespace
+
+// sort_bsbm / sort_bsbm_byrow / sort_bsdm on a HOST BlockedSBM / BlockedSDM, done on the device: the blocks are
+// uploaded back to back, every entry gets the key (block, in-block key), one radix sort orders all blocks at once (the
+// block id in the high bits keeps every entry inside its block), and the arrays go back into the caller's per-block
+// storage.  Same order as the host routine whenever coordinates inside a block are unique (equal keys keep input order).
+extern "C" int fsb_sort_blocked(int nrow, int ncol, int nblocks, const int* start_row, const int* blk_nnz, int* const* rows,
+                                int* const* cols, double* const* vals, int order) {
+  FSB_TRY(fsb_require_device());
+  if (nblocks < 0 || (order != 1 && order != 2) || (nblocks > 0 && (!start_row || !blk_nnz || !rows || !cols)))
+    return fsb_set_error(FSB_EINVAL, "fsb_sort_blocked: bad arguments");
+  std::vector<long> off((size_t)nblocks + 1, 0);
+  int max_rows = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    if (blk_nnz[b] < 0 || start_row[b + 1] < start_row[b]) return fsb_set_error(FSB_EINVAL, "fsb_sort_blocked: bad block metadata");
+    off[b + 1] = off[b] + blk_nnz[b];
+    max_rows = std::max(max_rows, start_row[b + 1] - start_row[b]);
+  }
+  const long nnz = off[nblocks];
+  if (nnz == 0) return FSB_OK;
+  if (nnz > (long)INT_MAX || nblocks >= (1 << 24)) return fsb_set_error(FSB_EINVAL, "fsb_sort_blocked: too many entries or blocks for the sort key");
+  {
+    long long n = 1; while (n < max_rows) n <<= 1;
+    const double lim = (double)(1ull << 40);
+    const double k1 = (double)n * (double)n * (double)(((long long)ncol + n - 1) / n), k2 = (double)max_rows * (double)ncol;
+    if ((order == 1 && k1 >= lim) || (order == 2 && k2 >= lim)) return fsb_set_error(FSB_EINVAL, "fsb_sort_blocked: in-block order key exceeds 40 bits");
+  }
+  cudaStream_t st = fsb_default_stream();
+  int *dr = nullptr, *dc = nullptr, *dr2 = nullptr, *dc2 = nullptr, *dsr = nullptr, *iota = nullptr, *perm = nullptr;
+  double *dv = nullptr, *dv2 = nullptr;
+  long* doff = nullptr;
+  unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int rc = FSB_OK;
+  auto A = [&](void** p, size_t bytes) { if (rc == FSB_OK && cudaMalloc(p, bytes) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__); };
+  A((void**)&dr, (size_t)nnz * 4); A((void**)&dc, (size_t)nnz * 4); A((void**)&dr2, (size_t)nnz * 4); A((void**)&dc2, (size_t)nnz * 4);
+  if (vals) { A((void**)&dv, (size_t)nnz * 8); A((void**)&dv2, (size_t)nnz * 8); }
+  A((void**)&dsr, ((size_t)nblocks + 1) * 4); A((void**)&doff, ((size_t)nblocks + 1) * 8);
+  A((void**)&keys, (size_t)nnz * 8); A((void**)&keys_sorted, (size_t)nnz * 8); A((void**)&iota, (size_t)nnz * 4); A((void**)&perm, (size_t)nnz * 4);
+  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
+    const size_t m = (size_t)blk_nnz[b];
+    if (!m) continue;
+    rc = fsb_h2d(dr + off[b], rows[b], m * 4, st);
+    if (rc == FSB_OK) rc = fsb_h2d(dc + off[b], cols[b], m * 4, st);
+    if (rc == FSB_OK && vals) rc = fsb_h2d(dv + off[b], vals[b], m * 8, st);
+  }
+  if (rc == FSB_OK) rc = fsb_h2d(dsr, start_row, ((size_t)nblocks + 1) * 4, st);
+  if (rc == FSB_OK) rc = fsb_h2d(doff, off.data(), ((size_t)nblocks + 1) * 8, st);
+  if (rc == FSB_OK) rc = fsb_check_index_range(dc, nnz, ncol, "column index", st);
+  if (rc == FSB_OK) rc = fsb_check_rows_in_blocks(dr, doff, dsr, nblocks, nnz, st);
+  if (rc == FSB_OK) {
+    host_blocked_sortkey_kernel<<<grid_for(nnz), 256, 0, st>>>(dr, dc, nnz, doff, dsr, nblocks, ncol, order, keys);
+    iota_kernel<<<grid_for(nnz), 256, 0, st>>>(iota, nnz);
+    fsb_count_launch(2);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, iota, perm, (long long)nnz, 0, 64, st);
+    cudaError_t e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, iota, perm, (long long)nnz, 0, 64, st);
+    fsb_count_launch(9);
+    if (e == cudaSuccess) {
+      gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(dr2, dr, perm, nnz);
+      gather_i32_kernel<<<grid_for(nnz), 256, 0, st>>>(dc2, dc, perm, nnz);
+      if (vals) gather_f64_kernel<<<grid_for(nnz), 256, 0, st>>>(dv2, dv, perm, nnz);
+      fsb_count_launch(vals ? 3 : 2);
+      e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_sort_blocked", __FILE__, __LINE__);
+  }
+  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
+    const size_t m = (size_t)blk_nnz[b];
+    if (!m) continue;
+    rc = fsb_d2h(rows[b], dr2 + off[b], m * 4, st);
+    if (rc == FSB_OK) rc = fsb_d2h(cols[b], dc2 + off[b], m * 4, st);
+    if (rc == FSB_OK && vals) rc = fsb_d2h(vals[b], dv2 + off[b], m * 8, st);
+  }
+  if (rc == FSB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "fsb_sort_blocked", __FILE__, __LINE__);
+  cudaFree(dr); cudaFree(dc); cudaFree(dr2); cudaFree(dc2); cudaFree(dv); cudaFree(dv2); cudaFree(dsr); cudaFree(doff);
+  cudaFree(keys); cudaFree(keys_sorted); cudaFree(iota); cudaFree(perm); cudaFree(tmp);
+  return rc;
+}
+
+// the drop-in's choice for sort_bsbm / sort_bsbm_byrow / sort_bsdm: device at >= FSB_SORT_DEVICE_MIN entries when a device
+// is present, else the bit-exact host routines block by block
+extern "C" int fsb_sort_blocked_auto(int nrow, int ncol, int nblocks, const int* start_row, const int* blk_nnz, int* const* rows,
+                                     int* const* cols, double* const* vals, int order) {
+  if (nblocks < 0 || (order != 1 && order != 2)) return fsb_set_error(FSB_EINVAL, "fsb_sort_blocked_auto: bad arguments");
+  static long min_dev = -1;
+  if (min_dev < 0) {
+    const char* e = getenv("FSB_SORT_DEVICE_MIN");
+    min_dev = e ? atol(e) : (1L << 20);
+  }
+  long nnz = 0;
+  for (int b = 0; b < nblocks; ++b) nnz += blk_nnz[b];
+  if (nnz >= min_dev && fsb_device_count() > 0) return fsb_sort_blocked(nrow, ncol, nblocks, start_row, blk_nnz, rows, cols, vals, order);
+  for (int b = 0; b < nblocks; ++b) {
+    const int rc = order == 1 ? fsb_host_sort_block_hilbert(start_row[b], start_row[b + 1] - start_row[b], blk_nnz[b], rows[b], cols[b], vals ? vals[b] : nullptr)
+                              : fsb_host_sort_block_byrow(ncol, blk_nnz[b], rows[b], cols[b]);
+    if (rc != FSB_OK) return rc;
+  }
+  return FSB_OK;
 }
 
 // what the drop-in sort_sbm / sort_sdm call: the device path for large matrices when a device is present, the

@@ -849,3 +849,38 @@ def test_device_global_hilbert_sort_matches_host(with_vals):
     with pytest.raises(fs.FsbError):
         bad = torch.tensor([0, 9], dtype=torch.int32, device="cuda")
         fs.check(fs.lib().fsb_sort_coo_hilbert_dev(4, 3, 2, bad.data_ptr(), bad.data_ptr(), None))
+
+
+@pytest.mark.parametrize("with_vals", [False, True])
+@pytest.mark.parametrize("order", [1, 2])
+def test_device_sort_of_host_blocked_structure_matches_host(with_vals, order):
+    """sort_bsbm / sort_bsbm_byrow / sort_bsdm on a HOST BlockedSBM / BlockedSDM through the device (one keyed radix sort
+    over all blocks, fsb_sort_blocked): the same per-block order as the host routines, block boundaries respected, a
+    ragged last block and empty blocks included, values carried."""
+    if with_vals and order == 2:
+        pytest.skip("the reference has no by-row sort for the double-valued format")
+    rng = np.random.default_rng(21 + order)
+    nrow, ncol, nnz, bs = 10_007, 5_000, 300_000, 512
+    flat = rng.choice(nrow * ncol, size=nnz, replace=False)
+    rows = (flat // ncol).astype(np.int32); cols = (flat % ncol).astype(np.int32)
+    rows[rows // bs == 3] = 4 * bs                      # block 3 becomes empty
+    flat2 = np.unique(rows.astype(np.int64) * ncol + cols)        # keep coordinates unique after the move
+    rows = (flat2 // ncol).astype(np.int32); cols = (flat2 % ncol).astype(np.int32)
+    perm = rng.permutation(rows.size); rows, cols = rows[perm], cols[perm]
+    vals = rng.random(rows.size) if with_vals else None
+    mk = (lambda: fs.new_bsdm(fs.new_sdm(nrow, ncol, rows.size, rows.copy(), cols.copy(), vals.copy()), bs)) if with_vals else \
+         (lambda: fs.new_bsbm(fs.new_sbm(nrow, ncol, rows.size, rows.copy(), cols.copy()), bs))
+    Bh, Bd = mk(), mk()
+    sort = fs.sort_bsbm if order == 1 else fs.sort_bsbm_byrow
+    sort(Bh, device=False)
+    sort(Bd, device=True)
+    assert Bh.nblocks == Bd.nblocks and int(Bh.nnz[3]) == 0
+    for b in range(Bh.nblocks):
+        assert np.array_equal(Bh.rows[b], Bd.rows[b]) and np.array_equal(Bh.cols[b], Bd.cols[b]), f"block {b}"
+        if with_vals:
+            assert np.array_equal(Bh.vals[b], Bd.vals[b]), f"values of block {b}"
+    # the product is unchanged by the re-ordering (test_sparse.c:372-377)
+    x = tvec(ncol); y = np.zeros(nrow); y2 = np.zeros(nrow)
+    (fs.bsdm_A_mul_B if with_vals else fs.bsbm_A_mul_B)(y, Bd, x)
+    (fs.bsdm_A_mul_B if with_vals else fs.bsbm_A_mul_B)(y2, mk(), x)
+    assert_close(y, y2, scale=2.0 * 64, what="product after the device sort")
