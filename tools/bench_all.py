@@ -165,11 +165,15 @@ def main():
         host_sort_s = time.perf_counter() - t0
         A_h = fs.new_sbm(N, F, ns, hr, hc)
         t0 = time.perf_counter(); B_h = fs.new_bsbm(A_h, 512); host_blk_s = time.perf_counter() - t0
-        t0 = time.perf_counter(); fs.sort_bsbm(B_h); host_bsort_s = time.perf_counter() - t0
+        B_d = fs.new_bsbm(A_h, 512)                       # the drop-in call on a HOST structure, through the device
+        t0 = time.perf_counter(); fs.sort_bsbm(B_h, device=False); host_bsort_s = time.perf_counter() - t0
+        t0 = time.perf_counter(); fs.sort_bsbm(B_d, device=True); dropin_dev_bsort_s = time.perf_counter() - t0
+        same = all(np.array_equal(B_h.rows[b], B_d.rows[b]) and np.array_equal(B_h.cols[b], B_d.cols[b]) for b in range(B_h.nblocks))
         emit(config="C4 preprocessing: sort_sbm -> new_bsbm(512) -> sort_bsbm", device_sort_sbm_s=sort_s, device_new_bsbm_plus_sort_bsbm_s=blk_s,
              device_total_s=sort_s + blk_s, host_sample_nnz=ns, host_sort_sbm_s_sample=host_sort_s, host_new_bsbm_s_sample=host_blk_s,
-             host_sort_bsbm_s_sample=host_bsort_s, host_total_s_scaled_to_full=(host_sort_s + host_blk_s + host_bsort_s) * (NNZ / ns))
-        del rs, cs, A_h, B_h, hr, hc
+             host_sort_bsbm_s_sample=host_bsort_s, host_total_s_scaled_to_full=(host_sort_s + host_blk_s + host_bsort_s) * (NNZ / ns),
+             dropin_sort_bsbm_on_host_struct_via_device_s_sample=dropin_dev_bsort_s, dropin_device_sort_matches_host=bool(same))
+        del rs, cs, A_h, B_h, B_d, hr, hc
         x = torch.randn(F, dtype=torch.float64, device="cuda"); y = torch.empty(N, dtype=torch.float64, device="cuda")
         ms = timed(lambda: Cb.spmm(x, 1, out=y), args.reps)
         ab = 4 * NNZ + 4 * (Cb.nblocks * N + 1) + 8 * N + 8 * F
