@@ -2,15 +2,18 @@
  *
  * Same struct layouts, function names and argument order as the reference, so callers
  * (test_sparse.c, bench_a_mul_b.c, preprocess.c, Macau-style samplers) recompile
- * unchanged.  Construction, loading and sorting are host code inside
- * libfastsparse_b200.so (bit-exact structure); every product forwards to the GPU
+ * unchanged.  Construction and loading are host code inside libfastsparse_b200.so
+ * (bit-exact structure); the Hilbert sorts run on the device above 2^20 entries (same
+ * order; host routine below that or without a GPU); every product forwards to the GPU
  * through the C ABI in ../fsb.h.  There is no CPU fallback: without a CUDA device a
  * product prints the library error and exits, the reference's own error convention
  * (sparse.h:115-118).
  *
  * Residency: the structs are caller-owned and their layout is frozen, so the HBM copy
  * of a matrix is tracked out of band by fsb_cache_*() (keyed by the array addresses
- * and a content fingerprint); entry points that mutate a structure drop its entry.
+ * and validated by a hash of the full content on every call -- the caller's arrays stay
+ * the source of truth, see FSB_DROPIN_CALL in ../fsb.h); entry points that mutate a
+ * structure drop its entry at once.
  */
 #ifndef SPARSE_H
 #define SPARSE_H
