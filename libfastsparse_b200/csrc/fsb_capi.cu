@@ -269,13 +269,12 @@ int fsb_blocked_upload(fsb_matrix_t* out, int nrow, int ncol, int nblocks, const
   if (rc == FSB_OK) rc = alloc((void**)&A->b_rows, n1 * 4);
   if (rc == FSB_OK) rc = alloc((void**)&A->b_cols, n1 * 4);
   if (rc == FSB_OK && vals) rc = alloc((void**)&A->b_vals, n1 * 8);
-  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
-    const size_t m = (size_t)blk_nnz[b];
-    if (!m) continue;
-    cudaError_t e = cudaMemcpyAsync(A->b_rows + off[b], rows[b], m * 4, cudaMemcpyHostToDevice, g_stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(A->b_cols + off[b], cols[b], m * 4, cudaMemcpyHostToDevice, g_stream);
-    if (e == cudaSuccess && vals) e = cudaMemcpyAsync(A->b_vals + off[b], vals[b], m * 8, cudaMemcpyHostToDevice, g_stream);
-    if (e != cudaSuccess) rc = fsb_cuda_error(e, "blocked upload", __FILE__, __LINE__);
+  if (rc == FSB_OK && nblocks > 0) {   // the per-block arrays, packed through the pinned ring (not one small copy per block)
+    std::vector<size_t> b4((size_t)nblocks), b8((size_t)nblocks);
+    for (int b = 0; b < nblocks; ++b) { b4[b] = (size_t)blk_nnz[b] * 4; b8[b] = (size_t)blk_nnz[b] * 8; }
+    rc = fsb_h2d_gather(A->b_rows, (const void* const*)rows, b4.data(), nblocks, g_stream);
+    if (rc == FSB_OK) rc = fsb_h2d_gather(A->b_cols, (const void* const*)cols, b4.data(), nblocks, g_stream);
+    if (rc == FSB_OK && vals) rc = fsb_h2d_gather(A->b_vals, (const void* const*)vals, b8.data(), nblocks, g_stream);
   }
   if (rc == FSB_OK) rc = fsb_check_index_range(A->b_rows, A->nnz, nrow, "row index", g_stream);
   if (rc == FSB_OK) rc = fsb_check_index_range(A->b_cols, A->nnz, ncol, "column index", g_stream);

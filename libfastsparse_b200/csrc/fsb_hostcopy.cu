@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 #include <emmintrin.h>
 #include <omp.h>
@@ -193,4 +194,84 @@ int fsb_d2h(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   const void* s[1] = {src};
   size_t b[1] = {bytes};
   return fsb_d2h_segments(1, d, s, b, nullptr, st);
+}
+
+// Many small host arrays <-> one contiguous device range (the per-block arrays of BlockedSBM / BlockedSDM: tens of
+// thousands of ~40 KB malloc'd pieces).  One cudaMemcpyAsync per piece from pageable memory costs ~8 us each; here the
+// pieces are packed into / unpacked from the pinned ring, so the DMA engine sees 4 MB transfers.
+namespace {
+struct Seg { const char* host; size_t ring_off, len; };
+}
+
+int fsb_h2d_gather(void* dst, const void* const* srcs, const size_t* bytes, long n, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  FSB_TRY(ring_init());
+  std::vector<Seg> segs;
+  size_t dev_off = 0, fill = 0;
+  long piece = 0;
+  auto flush = [&]() -> int {
+    if (!fill) return FSB_OK;
+    const int k = (int)(piece % kBuffers);
+    if (piece >= kBuffers) FSB_CUDA(cudaEventSynchronize(g_ring.ev[k]));     // the copy that last used this buffer
+    char* buf = g_ring.buf[k];
+    const long ns = (long)segs.size();
+#pragma omp parallel for num_threads(copy_threads()) schedule(static) if (fill >= ((size_t)1 << 20))
+    for (long i = 0; i < ns; ++i) memcpy(buf + segs[(size_t)i].ring_off, segs[(size_t)i].host, segs[(size_t)i].len);
+    FSB_CUDA(cudaMemcpyAsync((char*)dst + dev_off, buf, fill, cudaMemcpyHostToDevice, st));
+    FSB_CUDA(cudaEventRecord(g_ring.ev[k], st));
+    dev_off += fill; fill = 0; segs.clear(); ++piece;
+    return FSB_OK;
+  };
+  for (long i = 0; i < n; ++i) {
+    size_t done = 0;
+    while (done < bytes[i]) {
+      const size_t take = std::min(bytes[i] - done, kBounceBytes - fill);
+      segs.push_back(Seg{(const char*)srcs[i] + done, fill, take});
+      fill += take; done += take;
+      if (fill == kBounceBytes) FSB_TRY(flush());
+    }
+  }
+  FSB_TRY(flush());
+  for (int i = 0; i < kBuffers; ++i) FSB_CUDA(cudaEventSynchronize(g_ring.ev[i]));
+  return FSB_OK;
+}
+
+int fsb_d2h_scatter(void* const* dsts, const void* src, const size_t* bytes, long n, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  FSB_TRY(ring_init());
+  size_t total = 0;
+  for (long i = 0; i < n; ++i) total += bytes[i];
+  const long npieces = (long)((total + kBounceBytes - 1) / kBounceBytes);
+  auto enqueue = [&](long p) -> cudaError_t {
+    const int k = (int)(p % kBuffers);
+    const size_t off = (size_t)p * kBounceBytes, len = std::min(kBounceBytes, total - off);
+    cudaError_t e = cudaMemcpyAsync(g_ring.buf[k], (const char*)src + off, len, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(g_ring.ev[k], st);
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  for (long p = 0; p < npieces && p < kBuffers && e == cudaSuccess; ++p) e = enqueue(p);
+  long arr = 0;          // walk the destination arrays in step with the pieces
+  size_t arr_done = 0;
+  for (long p = 0; p < npieces && e == cudaSuccess; ++p) {
+    const int k = (int)(p % kBuffers);
+    e = cudaEventSynchronize(g_ring.ev[k]);
+    if (e != cudaSuccess) break;
+    const size_t len = std::min(kBounceBytes, total - (size_t)p * kBounceBytes);
+    std::vector<Seg> segs;
+    size_t off = 0;
+    while (off < len) {
+      while (arr < n && arr_done == bytes[arr]) { ++arr; arr_done = 0; }
+      const size_t take = std::min(bytes[arr] - arr_done, len - off);
+      segs.push_back(Seg{(const char*)dsts[arr] + arr_done, off, take});
+      arr_done += take; off += take;
+    }
+    const char* buf = g_ring.buf[k];
+    const long ns = (long)segs.size();
+#pragma omp parallel for num_threads(copy_threads()) schedule(static) if (len >= ((size_t)1 << 20))
+    for (long i = 0; i < ns; ++i) memcpy(const_cast<char*>(segs[(size_t)i].host), buf + segs[(size_t)i].ring_off, segs[(size_t)i].len);
+    if (p + kBuffers < npieces) e = enqueue(p + kBuffers);
+  }
+  if (e != cudaSuccess) return fsb_cuda_error(e, "fsb_d2h_scatter", __FILE__, __LINE__);
+  return FSB_OK;
 }

@@ -106,6 +106,9 @@ static inline cudaStream_t fsb_pick_stream(void* s) {
 bool fsb_host_is_pageable(const void* p);
 int fsb_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
 int fsb_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);
+// many small host arrays <-> one contiguous device range, packed through the pinned ring (blocked formats' per-block arrays)
+int fsb_h2d_gather(void* dst_dev, const void* const* srcs_host, const size_t* bytes, long n, cudaStream_t st);
+int fsb_d2h_scatter(void* const* dsts_host, const void* src_dev, const size_t* bytes, long n, cudaStream_t st);
 int fsb_d2h_segments(int nseg, void* const* dst_host, const void* const* src_dev, const size_t* bytes, const cudaEvent_t* ready,
                      cudaStream_t st);
 

@@ -787,13 +787,11 @@ extern "C" int fsb_sort_blocked(int nrow, int ncol, int nblocks, const int* star
   if (vals) { A((void**)&dv, (size_t)nnz * 8); A((void**)&dv2, (size_t)nnz * 8); }
   A((void**)&dsr, ((size_t)nblocks + 1) * 4); A((void**)&doff, ((size_t)nblocks + 1) * 8);
   A((void**)&keys, (size_t)nnz * 8); A((void**)&keys_sorted, (size_t)nnz * 8); A((void**)&iota, (size_t)nnz * 4); A((void**)&perm, (size_t)nnz * 4);
-  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
-    const size_t m = (size_t)blk_nnz[b];
-    if (!m) continue;
-    rc = fsb_h2d(dr + off[b], rows[b], m * 4, st);
-    if (rc == FSB_OK) rc = fsb_h2d(dc + off[b], cols[b], m * 4, st);
-    if (rc == FSB_OK && vals) rc = fsb_h2d(dv + off[b], vals[b], m * 8, st);
-  }
+  std::vector<size_t> b4((size_t)nblocks), b8((size_t)nblocks);
+  for (int b = 0; b < nblocks; ++b) { b4[b] = (size_t)blk_nnz[b] * 4; b8[b] = (size_t)blk_nnz[b] * 8; }
+  if (rc == FSB_OK) rc = fsb_h2d_gather(dr, (const void* const*)rows, b4.data(), nblocks, st);
+  if (rc == FSB_OK) rc = fsb_h2d_gather(dc, (const void* const*)cols, b4.data(), nblocks, st);
+  if (rc == FSB_OK && vals) rc = fsb_h2d_gather(dv, (const void* const*)vals, b8.data(), nblocks, st);
   if (rc == FSB_OK) rc = fsb_h2d(dsr, start_row, ((size_t)nblocks + 1) * 4, st);
   if (rc == FSB_OK) rc = fsb_h2d(doff, off.data(), ((size_t)nblocks + 1) * 8, st);
   if (rc == FSB_OK) rc = fsb_check_index_range(dc, nnz, ncol, "column index", st);
@@ -815,13 +813,9 @@ extern "C" int fsb_sort_blocked(int nrow, int ncol, int nblocks, const int* star
     }
     if (e != cudaSuccess) rc = fsb_cuda_error(e, "fsb_sort_blocked", __FILE__, __LINE__);
   }
-  for (int b = 0; rc == FSB_OK && b < nblocks; ++b) {
-    const size_t m = (size_t)blk_nnz[b];
-    if (!m) continue;
-    rc = fsb_d2h(rows[b], dr2 + off[b], m * 4, st);
-    if (rc == FSB_OK) rc = fsb_d2h(cols[b], dc2 + off[b], m * 4, st);
-    if (rc == FSB_OK && vals) rc = fsb_d2h(vals[b], dv2 + off[b], m * 8, st);
-  }
+  if (rc == FSB_OK) rc = fsb_d2h_scatter((void* const*)rows, dr2, b4.data(), nblocks, st);
+  if (rc == FSB_OK) rc = fsb_d2h_scatter((void* const*)cols, dc2, b4.data(), nblocks, st);
+  if (rc == FSB_OK && vals) rc = fsb_d2h_scatter((void* const*)vals, dv2, b8.data(), nblocks, st);
   if (rc == FSB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fsb_cuda_error(cudaGetLastError(), "fsb_sort_blocked", __FILE__, __LINE__);
   cudaFree(dr); cudaFree(dc); cudaFree(dr2); cudaFree(dc2); cudaFree(dv); cudaFree(dv2); cudaFree(dsr); cudaFree(doff);
   cudaFree(keys); cudaFree(keys_sorted); cudaFree(iota); cudaFree(perm); cudaFree(tmp);
