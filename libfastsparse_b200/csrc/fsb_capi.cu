@@ -434,8 +434,11 @@ static int spmv_t_xblocked(fsb_matrix* A, double* dY, const double* dX, cudaStre
   return FSB_OK;
 }
 
+// threshold and block size from profiles/r2p_xblock_threshold.jsonl (double CSR, 20 entries per row): the plain transpose wins
+// up to a 32 MB operand (0.389 vs 0.418 ms), the x-blocked one from 40 MB (0.524 vs 0.543), by 26 % at 80 MB; 32 MB blocks
+// beat 16 / 24 / 48 MB ones
 static bool use_xblocked_t(const fsb_matrix* A, int R) {
-  return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 48 << 10) << 10) && fsb_knob("t_xblock", 1);
+  return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 36 << 10) << 10) && fsb_knob("t_xblock", 1);
 }
 
 extern "C" {

@@ -800,7 +800,7 @@ def test_xblocked_transposed_spmv_matches_the_plain_transpose(with_vals):
         blocked = M.spmm_t(xd, 1).cpu().numpy()
         z = M.ata(torch.from_numpy(tvec(ncol)).cuda(), 1, lam=0.5).cpu().numpy()
     finally:
-        fs.check(L.fsb_tune(b"t_xblock_min_kb", 48 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
+        fs.check(L.fsb_tune(b"t_xblock_min_kb", 36 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
     want = oracle.coo_mul(nrow, rows, cols, vals, x, transpose=True, ncol=ncol)
     scale = 2.0 * float(np.bincount(cols, minlength=ncol).max())
     assert_close(blocked, want, scale=scale, what="x-blocked A'x vs oracle")
