@@ -45,6 +45,14 @@ def main():
         # rows that straddle tile boundaries differently in the shard, so compare to rounding there
         out[tag + "_Ax_slab_equal"] = bool(torch.equal(Ys, Y[r0 * R: r1 * R])) if R >= 2 else \
             bool(torch.allclose(Ys, Y[r0 * R: r1 * R], rtol=1e-13, atol=1e-12))
+        # the host-pointer product on a sharded handle: every rank uploads 1/G of X, the rest arrives by all-gather
+        if R >= 2:
+            import ctypes as C
+            import numpy as np
+            Xh = X.cpu().numpy(); Yh = np.zeros((r1 - r0) * R)
+            fs.check(fs.lib().fsb_spmm_host(shard.h, Yh.ctypes.data_as(C.POINTER(C.c_double)), Xh.ctypes.data_as(C.POINTER(C.c_double)), R))
+            out[tag + "_Ax_host_sharded_upload_equal"] = bool(np.array_equal(Yh, Ys.cpu().numpy()))
+            ok &= out[tag + "_Ax_host_sharded_upload_equal"]
         # A' x: allreduce of partials inside the library
         Z = full.spmm_t(Xt, R)
         Zs = shard.spmm_t(Xt[r0 * R: r1 * R].contiguous(), R)
