@@ -884,3 +884,31 @@ def test_device_sort_of_host_blocked_structure_matches_host(with_vals, order):
     (fs.bsdm_A_mul_B if with_vals else fs.bsbm_A_mul_B)(y, Bd, x)
     (fs.bsdm_A_mul_B if with_vals else fs.bsbm_A_mul_B)(y2, mk(), x)
     assert_close(y, y2, scale=2.0 * 64, what="product after the device sort")
+
+
+def test_round2_paths_on_degenerate_inputs():
+    """Empty and minimal inputs through the paths added in round 2: device sorts with no entries, the x-blocked
+    transpose of a matrix with a single column / no entries, a one-block operand."""
+    import torch
+    L = fs.lib()
+    z = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fs.check(L.fsb_sort_coo_hilbert_dev(5, 7, 0, z.data_ptr(), z.data_ptr(), None))            # nothing to sort
+    e = np.zeros(0, np.int32)
+    fs.check(L.fsb_sort_coo_hilbert(5, 7, 0, fs.api._ip(e), fs.api._ip(e), None))
+    B = fs.new_bsbm(fs.new_sbm(6, 4, 0, e.copy(), e.copy()), 4)                                 # blocked structure without entries
+    fs.sort_bsbm(B, device=True)
+    y = np.ones(6); fs.bsbm_A_mul_B(y, B, np.ones(4)); assert not y.any()
+    fs.check(L.fsb_tune(b"t_xblock_min_kb", 1)); fs.check(L.fsb_tune(b"t_xblock_kb", 1))
+    try:
+        # one column: every cell row of the blocked transpose belongs to column 0
+        nrow = 3000
+        rows = np.arange(0, nrow, 3, dtype=np.int32); cols = np.zeros(rows.size, np.int32); vals = 1.0 + np.arange(rows.size)
+        M = fs.DeviceMatrix.from_coo_tensors(nrow, 1, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), torch.from_numpy(vals).cuda())
+        x = torch.from_numpy(tvec(nrow)).cuda()
+        got = M.spmm_t(x, 1).cpu().numpy()
+        assert_close(got, [float(np.dot(vals, tvec(nrow)[rows]))], scale=2.0 * vals.sum(), what="x-blocked A'x, one column")
+        # no entries at all
+        M0 = fs.DeviceMatrix.from_coo_tensors(nrow, 5, z[:0], z[:0], None)
+        assert not M0.spmm_t(x, 1).cpu().numpy().any()
+    finally:
+        fs.check(L.fsb_tune(b"t_xblock_min_kb", 36 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
