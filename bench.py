@@ -403,6 +403,13 @@ def run_ours(args):
                     "pageable_check_max_abs": pageable_parity},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if world > 1:
+            # context only: the single-GPU ncu traffic of the same kernel build, assumed to split evenly over the row shards
+            t1, src1 = traffic_for(args.workload, kernel, passes)
+            if t1:
+                line["roofline"]["estimate_from_1gpu_capture"] = {
+                    "traffic": t1, "achieved": t1 / t_s / 1e9, "frac": t1 / t_s / 1e9 / (peak * world),
+                    "note": "NOT measured at this N: " + src1 + "; every shard runs the same kernel on 1/N of the rows against the full X"}
         line.update(extras)
         if world == 1 and not args.no_cpu:
             # the C caller: tests/_build/time_dropin (struct BinaryCSR + malloc'd operands + bcsr_A_mul_Bn through the header)
