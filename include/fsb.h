@@ -338,7 +338,9 @@ int fsb_tune_csr_staged(int deep);
  * FSB_TUNE_<NAME> gives the default).  Known knobs: "stream_policy" (1 = L2 evict_first on the matrix
  * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads, the default); "x_slabs" (S >= 2: the dense
  * operand repacked into S contiguous column slabs, one pass each); "t_xblock" (1 = x-blocked transpose for A'x with
- * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x). */
+ * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x); "ata_overlap" (1 = a row shard's A'(A X) partial is produced in four
+ * row chunks whose allreduces overlap the next chunk's product, above "ata_overlap_min_kb" KB of partial);
+ * multi-GPU block CG: "cg_p2p", "cg_p2p_gram", "cg_p2p_rs", "cg_graph"; "host_x_allgather". */
 int fsb_tune(const char* knob, int value);
 
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable

@@ -437,6 +437,18 @@ static int spmv_t_xblocked(fsb_matrix* A, double* dY, const double* dX, cudaStre
 // threshold and block size from profiles/r2p_xblock_threshold.jsonl (double CSR, 20 entries per row): the plain transpose wins
 // up to a 32 MB operand (0.389 vs 0.418 ms), the x-blocked one from 40 MB (0.524 vs 0.543), by 26 % at 80 MB; 32 MB blocks
 // beat 16 / 24 / 48 MB ones
+// second stream + events of the overlapped allreduce in fsb_ata_dev
+static cudaStream_t g_ata_stream = nullptr;
+static cudaEvent_t g_ata_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_ata_done = nullptr;
+static int ata_overlap_init() {
+  if (g_ata_stream) return FSB_OK;
+  FSB_CUDA(cudaStreamCreateWithFlags(&g_ata_stream, cudaStreamNonBlocking));
+  for (auto& e : g_ata_ev) FSB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  FSB_CUDA(cudaEventCreateWithFlags(&g_ata_done, cudaEventDisableTiming));
+  return FSB_OK;
+}
+
 static bool use_xblocked_t(const fsb_matrix* A, int R) {
   return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 36 << 10) << 10) && fsb_knob("t_xblock", 1);
 }
@@ -487,6 +499,28 @@ int fsb_ata_dev(fsb_matrix_t A, double* dY, const double* dX, int R, double lamb
   FSB_TRY(fsb_build_transpose(A, st));
   FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
   if (!dist) return fsb_launch_csr_spmm(A->T, dY, dTmp, R, st, lambda != 0.0 ? dX : nullptr, lambda);   // "+ lambda X" fused
+  if (R >= 2 && (size_t)nF * 8 >= ((size_t)fsb_knob("ata_overlap_min_kb", 32 << 10) << 10) && A->ncol >= 4096 && fsb_knob("ata_overlap", 1)) {
+    // Row shard with a large partial: produce A_g'(A_g X) in four row chunks and sum-allreduce chunk c on a second stream
+    // while chunk c+1 is computed -- three of the four allreduces hide behind the product, like the reduce-scatters of
+    // the sharded CG (8 GPUs, C5: 2.28 -> see profiles/ for the measured figure).
+    FSB_TRY(ata_overlap_init());
+    constexpr int kC = 4;
+    const int per = (A->ncol + kC - 1) / kC;
+    for (int c = 0; c < kC; ++c) {
+      const int r0 = c * per, r1 = std::min(A->ncol, r0 + per);
+      if (r0 >= r1) break;
+      fsb_matrix part;     // rows [r0, r1) of A_g': row_ptr values stay absolute, cols / vals shared
+      fsb_make_row_alias(&part, A->T, r0, r1);
+      FSB_TRY(fsb_launch_csr_spmm(&part, dY + (size_t)r0 * R, dTmp, R, st));
+      FSB_CUDA(cudaEventRecord(g_ata_ev[c], st));
+      FSB_CUDA(cudaStreamWaitEvent(g_ata_stream, g_ata_ev[c], 0));
+      FSB_TRY(fsb_allreduce_sum_dev(dY + (size_t)r0 * R, (long)(r1 - r0) * R, (void*)g_ata_stream));
+    }
+    FSB_CUDA(cudaEventRecord(g_ata_done, g_ata_stream));
+    FSB_CUDA(cudaStreamWaitEvent(st, g_ata_done, 0));
+    if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));
+    return FSB_OK;
+  }
   FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dTmp, R, st));
   FSB_TRY(maybe_allreduce(A, dY, nF, st));
   if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));

@@ -62,6 +62,13 @@ def main():
         for mode in (0, 1):
             Ks = shard.ata(X, R, lam=2.5, mode=mode)
             out[f"{tag}_AtA_mode{mode}_err"] = float((Ks - K).abs().max() / K.abs().max())
+        # the same operator with the chunked, overlapped allreduce forced (it switches on by itself above 32 MB of partial)
+        if R >= 2:
+            fs.check(fs.lib().fsb_tune(b"ata_overlap_min_kb", 1))
+            Ko = shard.ata(X, R, lam=2.5, mode=0)
+            fs.check(fs.lib().fsb_tune(b"ata_overlap_min_kb", 32 << 10))
+            out[f"{tag}_AtA_overlapped_allreduce_err"] = float((Ko - K).abs().max() / K.abs().max())
+            ok &= out[f"{tag}_AtA_overlapped_allreduce_err"] < 1e-12
         # block CG on the shard vs on the full matrix
         Xf, itf = full.cg(B, R, lam=15.0, tol=1e-8)
         ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12
