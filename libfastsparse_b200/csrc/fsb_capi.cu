@@ -449,6 +449,32 @@ static int ata_overlap_init() {
   return FSB_OK;
 }
 
+static bool use_overlapped_allreduce(const fsb_matrix* A, int R) {
+  return A->sharded && fsb_comm_active() && R >= 2 && A->ncol >= 4096 && fsb_knob("ata_overlap", 1) &&
+         (size_t)A->ncol * R * 8 >= ((size_t)fsb_knob("ata_overlap_min_kb", 32 << 10) << 10);
+}
+
+// dY[ncol][R] = sum over ranks of A_g' dT (A->T built): four row chunks of A_g', chunk c's sum-allreduce on a second
+// stream while chunk c+1 is computed; st continues once every chunk is reduced
+static int spmm_t_overlapped_allreduce(fsb_matrix* A, double* dY, const double* dT, int R, cudaStream_t st) {
+  FSB_TRY(ata_overlap_init());
+  constexpr int kC = 4;
+  const int per = (A->ncol + kC - 1) / kC;
+  for (int c = 0; c < kC; ++c) {
+    const int r0 = c * per, r1 = std::min(A->ncol, r0 + per);
+    if (r0 >= r1) break;
+    fsb_matrix part;     // rows [r0, r1) of A_g': row_ptr values stay absolute, cols / vals shared
+    fsb_make_row_alias(&part, A->T, r0, r1);
+    FSB_TRY(fsb_launch_csr_spmm(&part, dY + (size_t)r0 * R, dT, R, st));
+    FSB_CUDA(cudaEventRecord(g_ata_ev[c], st));
+    FSB_CUDA(cudaStreamWaitEvent(g_ata_stream, g_ata_ev[c], 0));
+    FSB_TRY(fsb_allreduce_sum_dev(dY + (size_t)r0 * R, (long)(r1 - r0) * R, (void*)g_ata_stream));
+  }
+  FSB_CUDA(cudaEventRecord(g_ata_done, g_ata_stream));
+  FSB_CUDA(cudaStreamWaitEvent(st, g_ata_done, 0));
+  return FSB_OK;
+}
+
 static bool use_xblocked_t(const fsb_matrix* A, int R) {
   return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 36 << 10) << 10) && fsb_knob("t_xblock", 1);
 }
@@ -471,6 +497,7 @@ int fsb_spmm_t_dev(fsb_matrix_t A, double* dY, const double* dX, int R, void* st
     return maybe_allreduce(A, dY, (long)A->ncol, st);
   }
   FSB_TRY(fsb_build_transpose(A, st));
+  if (use_overlapped_allreduce(A, R)) return spmm_t_overlapped_allreduce(A, dY, dX, R, st);
   FSB_TRY(fsb_launch_csr_spmm(A->T, dY, dX, R, st));
   return maybe_allreduce(A, dY, (long)A->ncol * R, st);
 }
@@ -499,25 +526,11 @@ int fsb_ata_dev(fsb_matrix_t A, double* dY, const double* dX, int R, double lamb
   FSB_TRY(fsb_build_transpose(A, st));
   FSB_TRY(fsb_launch_csr_spmm(A, dTmp, dX, R, st));
   if (!dist) return fsb_launch_csr_spmm(A->T, dY, dTmp, R, st, lambda != 0.0 ? dX : nullptr, lambda);   // "+ lambda X" fused
-  if (R >= 2 && (size_t)nF * 8 >= ((size_t)fsb_knob("ata_overlap_min_kb", 32 << 10) << 10) && A->ncol >= 4096 && fsb_knob("ata_overlap", 1)) {
+  if (use_overlapped_allreduce(A, R)) {
     // Row shard with a large partial: produce A_g'(A_g X) in four row chunks and sum-allreduce chunk c on a second stream
     // while chunk c+1 is computed -- three of the four allreduces hide behind the product, like the reduce-scatters of
     // the sharded CG (8 GPUs, C5: 2.28 -> see profiles/ for the measured figure).
-    FSB_TRY(ata_overlap_init());
-    constexpr int kC = 4;
-    const int per = (A->ncol + kC - 1) / kC;
-    for (int c = 0; c < kC; ++c) {
-      const int r0 = c * per, r1 = std::min(A->ncol, r0 + per);
-      if (r0 >= r1) break;
-      fsb_matrix part;     // rows [r0, r1) of A_g': row_ptr values stay absolute, cols / vals shared
-      fsb_make_row_alias(&part, A->T, r0, r1);
-      FSB_TRY(fsb_launch_csr_spmm(&part, dY + (size_t)r0 * R, dTmp, R, st));
-      FSB_CUDA(cudaEventRecord(g_ata_ev[c], st));
-      FSB_CUDA(cudaStreamWaitEvent(g_ata_stream, g_ata_ev[c], 0));
-      FSB_TRY(fsb_allreduce_sum_dev(dY + (size_t)r0 * R, (long)(r1 - r0) * R, (void*)g_ata_stream));
-    }
-    FSB_CUDA(cudaEventRecord(g_ata_done, g_ata_stream));
-    FSB_CUDA(cudaStreamWaitEvent(st, g_ata_done, 0));
+    FSB_TRY(spmm_t_overlapped_allreduce(A, dY, dTmp, R, st));
     if (lambda != 0.0) FSB_TRY(fsb_dense_axpy_lambda(dY, dX, lambda, nF, st));
     return FSB_OK;
   }

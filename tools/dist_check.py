@@ -66,9 +66,11 @@ def main():
         if R >= 2:
             fs.check(fs.lib().fsb_tune(b"ata_overlap_min_kb", 1))
             Ko = shard.ata(X, R, lam=2.5, mode=0)
+            Zo = shard.spmm_t(Xt[r0 * R: r1 * R].contiguous(), R)
             fs.check(fs.lib().fsb_tune(b"ata_overlap_min_kb", 32 << 10))
             out[f"{tag}_AtA_overlapped_allreduce_err"] = float((Ko - K).abs().max() / K.abs().max())
-            ok &= out[f"{tag}_AtA_overlapped_allreduce_err"] < 1e-12
+            out[f"{tag}_Atx_overlapped_allreduce_err"] = float((Zo - Z).abs().max() / Z.abs().max())
+            ok &= out[f"{tag}_AtA_overlapped_allreduce_err"] < 1e-12 and out[f"{tag}_Atx_overlapped_allreduce_err"] < 1e-12
         # block CG on the shard vs on the full matrix
         Xf, itf = full.cg(B, R, lam=15.0, tol=1e-8)
         ok &= out[tag + "_Ax_slab_equal"] and out[tag + "_Atx_err"] < 1e-12
