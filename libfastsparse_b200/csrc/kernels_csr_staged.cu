@@ -272,6 +272,10 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
   size_t body = std::max((size_t)(CAP + 16) * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging (+ alignment / vector-read slack) or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
   if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {   // experiment knob: shared-memory carve-out in percent of the maximum (-1: the driver's choice)
+    const int co = fsb_knob("staged_carveout", -1);
+    if (co >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+  }
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
   kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, ldx, xcol0);
   return FSB_OK;

@@ -8,13 +8,16 @@
 // transpose of a power-law matrix) serialise a CTA.  Here the work is split by ENTRIES, not
 // rows (merge-path, Merrill & Garland): CTA b takes items [bT, (b+1)T) of the merged list
 // (row ends, entries); its two end points are found by binary search in row_ptr.
-//   1. all 256 threads load the CTA's run of cols/vals with coalesced loads and write the
-//      products x[col]*val into shared memory: gather parallelism is independent of rows;
+//   1. the CTA's run of cols/vals comes into shared memory -- R = 1: by two TMA bulk copies (csr_stream_tma_kernel,
+//      the default), otherwise by coalesced per-thread loads -- all 256 threads gather x[col] and leave the products
+//      x[col]*val in shared memory: gather parallelism is independent of rows;
 //   2. one thread per row that ENDS in the tile sums its segment in stored order and stores
 //      Y[row];
 //   3. the piece of the row that continues into the next tile goes to a carry slot; a tiny
 //      fix-up kernel adds the carries in tile order.  Deterministic, no atomics, perfectly
 //      balanced for any row-length distribution, empty rows included.
+#include <stdint.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -58,72 +61,14 @@ __global__ void merge_splits_kernel(int nrow, long long nnz, const int* __restri
   split[b] = merge_search(row_ptr, nrow, nnz, d);
 }
 
-// MINB = minimum resident CTAs per SM promised to ptxas.  Without one it budgets 32 registers and serialises the PER
-// independent loads.  Two builds: 6 CTAs/SM (42 registers) is 11 % faster when the dense operand is small and mostly
-// hits in cache (C3 double SpMV, x = 8 MB: 0.97 vs 1.08 ms), 4 CTAs/SM (56 registers, all loads of a thread in flight)
-// is 13 % faster when it is large (the transpose, x = 80 MB: 1.31 vs 1.48 ms).  The launcher picks by operand size.
-// POL (knob "stream_policy", off by default): L2 cache-policy words on the loads -- the matrix stream (cols / vals,
-// touched once) evict_first, the gathered dense operand evict_last, like the staged kernel (fsb_device.cuh).
-template <int RT, bool VALS, int MINB, bool POL>
-__global__ void __launch_bounds__(kThreads, MINB)
-csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
-                  const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
-                  const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {
-  constexpr int kTile = Tile<RT>::n;
-  __shared__ int s_end[kTile + 1];
-  __shared__ double s_p[kTile * RT];
+// Phase 2 and 3 of a tile: rows ending in the tile are summed from the products in shared memory (sp[t * RT + q] for
+// entry t of the tile), the piece of the row that continues into the next tile becomes the tile's carry.
+template <int RT>
+__device__ __forceinline__ void reduce_tile(const double* __restrict__ s_p, const int* __restrict__ s_end, long long j0, int i0, int i1,
+                                            int ndone, int nn, int nrow, double* __restrict__ Y, int* __restrict__ carry_row,
+                                            double* __restrict__ carry_val) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const long long total = (long long)nrow + nnz;
-  const long long d0 = (long long)blockIdx.x * kTile;
-  const long long d1 = min(d0 + kTile, total);
-  const int i0 = __ldg(split + blockIdx.x), i1 = __ldg(split + blockIdx.x + 1);
-  const long long j0 = d0 - i0, j1 = d1 - i1;
-  const int ndone = i1 - i0;            // rows whose end falls in this tile
-  const int nn = (int)(j1 - j0);        // entries in this tile
-  const int nend = ndone + (i1 < nrow ? 1 : 0);
-  for (int k = tid; k < nend; k += kThreads) s_end[k] = __ldg(row_ptr + i0 + 1 + k);
-  {
-    // all of this thread's entries are loaded before any gather is issued, and all gathers
-    // before any product is stored: PER independent loads in flight per thread in each phase
-    constexpr int PER = kTile / kThreads;
-    int c[PER];
-    double v[PER];
-    double xv[PER][RT];
-    unsigned long long pol_stream = 0, pol_keep = 0;
-    if (POL) { pol_stream = make_l2_policy(2); pol_keep = make_l2_policy(1); }
-#pragma unroll
-    for (int p = 0; p < PER; ++p) {
-      const int t = tid + p * kThreads;
-      c[p] = 0;
-      v[p] = 1.0;
-      if (t < nn) {
-        c[p] = POL ? ld_stream_s32_pol(cols + j0 + t, pol_stream) : ld_stream_s32(cols + j0 + t);
-        if (VALS) v[p] = POL ? ld_stream_f64_pol(vals + j0 + t, pol_stream) : ld_stream_f64(vals + j0 + t);
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < PER; ++p) {
-      const int t = tid + p * kThreads;
-#pragma unroll
-      for (int k = 0; k < RT; ++k) {
-        xv[p][k] = 0.0;
-        if (t < nn) {
-          if (POL) XLoad<1>::ldp(&xv[p][k], X + (long long)c[p] * RT + k, pol_keep);
-          else xv[p][k] = __ldg(X + (long long)c[p] * RT + k);
-        }
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < PER; ++p) {
-      const int t = tid + p * kThreads;
-      if (t < nn) {
-#pragma unroll
-        for (int k = 0; k < RT; ++k) s_p[t * RT + k] = VALS ? xv[p][k] * v[p] : xv[p][k];
-      }
-    }
-  }
-  __syncthreads();
   // rows ending in this tile: GL lanes per row chosen from the tile's mean row length
   // (1 lane for short rows -- a shuffle tree per 20-entry row costs more than the sum itself --
   // 8 lanes up to ~128 entries, a full warp beyond); lanes stride over the segment and are
@@ -180,6 +125,137 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
   }
 }
 
+// MINB = minimum resident CTAs per SM promised to ptxas.  Without one it budgets 32 registers and serialises the PER
+// independent loads.  Two builds: 6 CTAs/SM (42 registers) is 11 % faster when the dense operand is small and mostly
+// hits in cache (C3 double SpMV, x = 8 MB: 0.97 vs 1.08 ms), 4 CTAs/SM (56 registers, all loads of a thread in flight)
+// is 13 % faster when it is large (the transpose, x = 80 MB: 1.31 vs 1.48 ms).  The launcher picks by operand size.
+// POL (knob "stream_policy", off by default): L2 cache-policy words on the loads -- the matrix stream (cols / vals,
+// touched once) evict_first, the gathered dense operand evict_last, like the staged kernel (fsb_device.cuh).
+template <int RT, bool VALS, int MINB, int POL>
+__global__ void __launch_bounds__(kThreads, MINB)
+csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                  const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                  const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {
+  constexpr int kTile = Tile<RT>::n;
+  __shared__ int s_end[kTile + 1];
+  __shared__ double s_p[kTile * RT];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const long long total = (long long)nrow + nnz;
+  const long long d0 = (long long)blockIdx.x * kTile;
+  const long long d1 = min(d0 + kTile, total);
+  const int i0 = __ldg(split + blockIdx.x), i1 = __ldg(split + blockIdx.x + 1);
+  const long long j0 = d0 - i0, j1 = d1 - i1;
+  const int ndone = i1 - i0;            // rows whose end falls in this tile
+  const int nn = (int)(j1 - j0);        // entries in this tile
+  const int nend = ndone + (i1 < nrow ? 1 : 0);
+  for (int k = tid; k < nend; k += kThreads) s_end[k] = __ldg(row_ptr + i0 + 1 + k);
+  {
+    // all of this thread's entries are loaded before any gather is issued, and all gathers
+    // before any product is stored: PER independent loads in flight per thread in each phase
+    constexpr int PER = kTile / kThreads;
+    int c[PER];
+    double v[PER];
+    double xv[PER][RT];
+    unsigned long long pol_stream = 0, pol_keep = 0;
+    if (POL == 1) { pol_stream = make_l2_policy(2); pol_keep = make_l2_policy(1); }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      c[p] = 0;
+      v[p] = 1.0;
+      if (t < nn) {
+        c[p] = POL == 1 ? ld_stream_s32_pol(cols + j0 + t, pol_stream) : ld_stream_s32(cols + j0 + t);
+        if (VALS) v[p] = POL == 1 ? ld_stream_f64_pol(vals + j0 + t, pol_stream) : ld_stream_f64(vals + j0 + t);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+#pragma unroll
+      for (int k = 0; k < RT; ++k) {
+        xv[p][k] = 0.0;
+        if (t < nn) {
+          if (POL == 1) XLoad<1>::ldp(&xv[p][k], X + (long long)c[p] * RT + k, pol_keep);
+          else xv[p][k] = __ldg(X + (long long)c[p] * RT + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      if (t < nn) {
+#pragma unroll
+        for (int k = 0; k < RT; ++k) s_p[t * RT + k] = VALS ? xv[p][k] * v[p] : xv[p][k];
+      }
+    }
+  }
+  __syncthreads();
+  reduce_tile<RT>(s_p, s_end, j0, i0, i1, ndone, nn, nrow, Y, carry_row, carry_val);
+}
+
+// ---- R = 1, TMA-fed form (default when the arrays sit on 16-byte boundaries).  The tile's run of column indices and
+// values comes into shared memory by two bulk copies (cp.async.bulk, SASS UBLKCP, completion on one mbarrier, L2
+// evict_first) instead of per-thread LDGs: the matrix stream no longer passes through L1TEX -- whose tag stage the
+// 8-byte gathers saturate (one wavefront per gather, profiles/r2_gather_ceiling.md) -- nor through registers, so the
+// kernel fits 32 registers and eight CTAs per SM.  A run starts at an arbitrary entry: each copy starts at the
+// enclosing 16-byte boundary and the entries are read at a shift (0..3 indices, 0..1 values).  The row ends share the
+// index buffer (a tile holds kTile merged items: nn entries + ndone row ends), the products overwrite the values in
+// place, so the footprint stays at 24.7 KB per CTA.
+template <bool VALS, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+csr_stream_tma_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
+                      const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
+                      const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val) {
+  constexpr int kTile = Tile<1>::n;
+  __shared__ __align__(16) int s_ci[kTile + 16];      // [index run from the 16-byte boundary | row ends]
+  __shared__ __align__(16) double s_pv[kTile + 4];    // values in, products out (same slots)
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int tid = threadIdx.x;
+  const long long total = (long long)nrow + nnz;
+  const long long d0 = (long long)blockIdx.x * kTile;
+  const long long d1 = min(d0 + kTile, total);
+  const int i0 = __ldg(split + blockIdx.x), i1 = __ldg(split + blockIdx.x + 1);
+  const long long j0 = d0 - i0, j1 = d1 - i1;
+  const int ndone = i1 - i0;
+  const int nn = (int)(j1 - j0);
+  const int nend = ndone + (i1 < nrow ? 1 : 0);
+  const int shc = (int)(j0 & 3), shv = (int)(j0 & 1);
+  const int ncw = (shc + nn + 3) & ~3;                // index slots the bulk copy fills
+  int* s_end = s_ci + ncw;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    if (nn > 0) {
+      const unsigned long long spol = make_l2_policy(2);
+      const unsigned bc = (unsigned)ncw * 4u;
+      const unsigned bv = VALS ? (unsigned)((shv + nn + 1) & ~1) * 8u : 0u;
+      mbar_expect_tx(&s_bar, bc + bv);
+      tma_load_1d(s_ci, cols + (j0 - shc), bc, &s_bar, spol);
+      if (VALS) tma_load_1d(s_pv, vals + (j0 - shv), bv, &s_bar, spol);
+    }
+  }
+  for (int k = tid; k < nend; k += kThreads) s_end[k] = __ldg(row_ptr + i0 + 1 + k);
+  __syncthreads();                                    // barrier initialised, row ends in place
+  if (nn > 0) mbar_wait(&s_bar, 0);
+  {
+    constexpr int PER = kTile / kThreads;
+    double xv[PER];
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      xv[p] = 0.0;
+      if (t < nn) xv[p] = __ldg(X + s_ci[shc + t]);
+    }
+#pragma unroll
+    for (int p = 0; p < PER; ++p) {
+      const int t = tid + p * kThreads;
+      if (t < nn) s_pv[shv + t] = VALS ? xv[p] * s_pv[shv + t] : xv[p];
+    }
+  }
+  __syncthreads();
+  reduce_tile<1>(s_pv + shv, s_end, j0, i0, i1, ndone, nn, nrow, Y, carry_row, carry_val);
+}
+
 // add the carried pieces to their rows, run by run, in tile order (deterministic)
 template <int RT>
 __global__ void csr_stream_fixup_kernel(int ntiles, const int* __restrict__ carry_row, const double* __restrict__ carry_val,
@@ -217,6 +293,28 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
     FSB_KERNEL_CHECK();
     A->split_tile = kTile;
   }
+  // R = 1: the TMA-fed form (knob "stream_tma", 0 = the per-thread-load form below)
+  if (RT == 1 && fsb_knob("stream_tma", 1) && !fsb_knob("stream_policy", 0) && ((uintptr_t)A->cols & 15) == 0 &&
+      (!VALS || ((uintptr_t)A->vals & 15) == 0)) {
+    // built for 6 CTAs per SM (40 registers) whatever the operand size.  The build for 8 (32 registers) is 1.6x SLOWER:
+    // eight 24.7 KB CTAs make the driver carve 228 KB of the SM's 256 KB out as shared memory, and a gather that misses L1
+    // holds a line there until its data returns -- with ~28 KB of L1 left the gathers in flight, hence the gather rate,
+    // collapse (profiles/r2w_l1_carveout.md).  Knob "stream_carveout": explicit carve-out in percent (-1: driver's choice).
+    const int minb = fsb_knob("stream_tma_minb", 6);
+    const int co = fsb_knob("stream_carveout", -1);
+#define FSB_TMA_LAUNCH(MINB_)                                                                                                \
+  do {                                                                                                                       \
+    if (co >= 0) cudaFuncSetAttribute(csr_stream_tma_kernel<VALS, MINB_>, cudaFuncAttributePreferredSharedMemoryCarveout, co); \
+    csr_stream_tma_kernel<VALS, MINB_><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, \
+                                                                    carry_row, carry_val);                                   \
+  } while (0)
+    if (minb >= 8) FSB_TMA_LAUNCH(8); else if (minb <= 4) FSB_TMA_LAUNCH(4); else FSB_TMA_LAUNCH(6);
+#undef FSB_TMA_LAUNCH
+    FSB_KERNEL_CHECK();
+    csr_stream_fixup_kernel<RT><<<(ntiles + 255) / 256, 256, 0, st>>>(ntiles, carry_row, carry_val, dY);
+    FSB_KERNEL_CHECK();
+    return FSB_OK;
+  }
   // bytes of the dense operand a wave of CTAs gathers from: the whole operand, or one block of it for an x-blocked transpose
   const double x_live = A->x_live_bytes > 0 ? (double)A->x_live_bytes : (double)A->ncol * RT * 8.0;
   const bool small_x = x_live <= 34e6;
@@ -227,8 +325,8 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
 #define FSB_STREAM_LAUNCH(MINB_, POL_)                                                                               \
   csr_stream_kernel<RT, VALS, MINB_, POL_><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, \
                                                                         A->split, carry_row, carry_val)
-  if (small_x) { if (pol) FSB_STREAM_LAUNCH(6, true); else FSB_STREAM_LAUNCH(6, false); }
-  else         { if (pol) FSB_STREAM_LAUNCH(4, true); else FSB_STREAM_LAUNCH(4, false); }
+  if (small_x) { if (pol) FSB_STREAM_LAUNCH(6, 1); else FSB_STREAM_LAUNCH(6, 0); }
+  else         { if (pol) FSB_STREAM_LAUNCH(4, 1); else FSB_STREAM_LAUNCH(4, 0); }
 #undef FSB_STREAM_LAUNCH
   FSB_KERNEL_CHECK();
   csr_stream_fixup_kernel<RT><<<(ntiles + 255) / 256, 256, 0, st>>>(ntiles, carry_row, carry_val, dY);

@@ -912,3 +912,36 @@ def test_round2_paths_on_degenerate_inputs():
         assert not M0.spmm_t(x, 1).cpu().numpy().any()
     finally:
         fs.check(L.fsb_tune(b"t_xblock_min_kb", 36 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
+
+
+@pytest.mark.parametrize("with_vals", [False, True])
+def test_stream_kernel_tma_fed_form_is_bit_identical_to_the_per_thread_load_form(with_vals):
+    """R = 1 merge-path kernel: the default brings a tile's run of indices / values into shared memory by TMA bulk copies
+    that start at the enclosing 16-byte boundary (kernels_csr_stream.cu csr_stream_tma_kernel); knob stream_tma = 0 is the
+    earlier per-thread-load form.  Both must give the same bits -- and the oracle's product -- on a matrix whose tiles
+    start at every alignment (ragged rows, empty rows, a 9000-entry row spanning several tiles, a last tile of a few
+    entries), through A x and the cached transpose."""
+    import torch
+    rng = np.random.default_rng(5 + with_vals)
+    nrow, ncol, nnz = 7001, 1913, 70_003
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=9000)
+    v = vals if with_vals else None
+    rp, cc, vv = oracle.csr_from_coo(nrow, rows, cols, v)
+    M = fs.DeviceMatrix.from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(),
+                                         torch.from_numpy(vals).cuda() if with_vals else None)
+    x = torch.from_numpy(tvec(ncol)).cuda(); xt = torch.from_numpy(tvec(nrow)).cuda()
+    L = fs.lib()
+    fs.check(L.fsb_tune_csr_algo(3, 0, 0))
+    try:
+        got = {}
+        for form in (1, 0):
+            fs.check(L.fsb_tune(b"stream_tma", form))
+            got[form] = (M.spmm(x, 1).cpu().numpy(), M.spmm_t(xt, 1).cpu().numpy())
+    finally:
+        fs.check(L.fsb_tune(b"stream_tma", 1)); fs.check(L.fsb_tune_csr_algo(0, 0, 0))
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    want = oracle.csr_mul(nrow, rp, cc, vv, tvec(ncol).reshape(-1, 1), 1).reshape(-1)
+    sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(tvec(ncol)).reshape(-1, 1), 1)).reshape(-1)
+    assert_close(got[1][0], want, sc, what="TMA-fed stream kernel vs oracle")
+    want_t = oracle.coo_mul(nrow, rows, cols, v, tvec(nrow), transpose=True, ncol=ncol)
+    assert_close(got[1][1], want_t, scale=2.0 * float(np.bincount(cols, minlength=ncol).max()), what="TMA-fed stream kernel, transpose, vs oracle")
