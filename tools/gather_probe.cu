@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(2); } } while (0)
 
@@ -152,6 +153,87 @@ static void run(const char* label, const int* idx, long ng, const double* tab, l
   CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
 }
 
+
+// ---- the same gathers through cp.async (LDGSTS, .cg = L2 only): every lane keeps D 16-byte slots of a shared-memory ring
+// in flight instead of U registers, so the data in flight is bounded by the ring (D x 4 KB per CTA), not by registers
+// or by the L1 lines a missing LDG holds.  B gathers per commit group, D / B groups in flight.
+template <int LPG, int D, int B>
+__global__ void __launch_bounds__(256) gather_async_kernel(const int* __restrict__ idx, long ngather, const double* __restrict__ tab, int rowd,
+                                                           double* __restrict__ out, unsigned long long* __restrict__ clk) {
+  const unsigned long long ps = policy(2);
+  const int sub = threadIdx.x % LPG, grp = threadIdx.x / LPG;
+  constexpr int NG = 256 / LPG;
+  constexpr int TILE = 2048;
+  extern __shared__ __align__(16) unsigned char smem[];
+  int* s_idx = reinterpret_cast<int*>(smem);
+  double2* ring = reinterpret_cast<double2*>(smem + TILE * 4);   // [D][256]
+  unsigned long long c0 = 0, t0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { c0 = clock64(); t0 = gtime(); }
+  double2 acc = make_double2(0.0, 0.0);
+  for (long base = (long)blockIdx.x * TILE; base < ngather; base += (long)gridDim.x * TILE) {
+    const int n = (int)min((long)TILE, ngather - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 256) s_idx[i] = ldi(idx + base + i, ps);
+    __syncthreads();
+    const int K = n > grp ? (n - grp + NG - 1) / NG : 0;       // this group's gathers: entries grp + k NG
+    auto issue = [&](int k0) {
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int k = k0 + u;
+        if (k < K) {
+          const int c = s_idx[grp + k * NG];
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + (k % D) * 256 + threadIdx.x);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(tab + (long)c * rowd + sub * 2) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int k0 = 0; k0 < D; k0 += B) issue(k0);
+    for (int k0 = 0; k0 < K; k0 += B) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(D / B - 1) : "memory");
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int k = k0 + u;
+        if (k < K) { const double2 v = ring[(k % D) * 256 + threadIdx.x]; acc.x += v.x; acc.y += v.y; }
+      }
+      issue(k0 + D);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  if (acc.x + acc.y == 1.2345e300) out[0] = acc.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { clk[0] = clock64() - c0; clk[1] = gtime() - t0; }
+}
+
+template <int LPG, int D, int B>
+static void run_async(const char* label, const int* idx, long ng, const double* tab, long table_bytes, int rowd, double* out,
+                      unsigned long long* clk, int ctas_per_sm) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int grid = 148 * ctas_per_sm;
+  const int smem = 2048 * 4 + D * 256 * 16;
+  CK(cudaFuncSetAttribute(gather_async_kernel<LPG, D, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int w = 0; w < 2; ++w) gather_async_kernel<LPG, D, B><<<grid, 256, smem>>>(idx, ng, tab, rowd, out, clk);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  unsigned long long h[2] = {0, 0}, hb[2] = {1, 1};
+  for (int it = 0; it < 5; ++it) {
+    CK(cudaEventRecord(e0));
+    gather_async_kernel<LPG, D, B><<<grid, 256, smem>>>(idx, ng, tab, rowd, out, clk);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost));
+    if (ms < best) { best = ms; hb[0] = h[0]; hb[1] = h[1]; }
+  }
+  const double gran = 16.0 * LPG, bytes = (double)ng * gran, mhz = (double)hb[0] / (double)hb[1] * 1e3;
+  printf("{\"probe\": \"%s\", \"path\": \"cp.async ring\", \"table_MB\": %.0f, \"gran_B\": %.0f, \"ring_depth\": %d, \"ctas_per_sm\": %d, "
+         "\"ring_kb_per_sm\": %d, \"ngather\": %ld, \"ms\": %.4f, \"gathered_TBs\": %.3f, \"sm_mhz_in_kernel\": %.0f}\n",
+         label, table_bytes / 1e6, gran, D, ctas_per_sm, D * 4 * ctas_per_sm, ng, best, bytes / (best * 1e-3) / 1e12, mhz);
+  fflush(stdout);
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+}
+
 int main(int argc, char** argv) {
   const long ng = (argc > 1 ? atol(argv[1]) : 200) * 1000000L;
   int* idx; double *tab, *out; unsigned long long* clk;
@@ -159,6 +241,34 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&idx, ng * 4)); CK(cudaMalloc(&tab, tab_max)); CK(cudaMalloc(&out, 64)); CK(cudaMalloc(&clk, 16));
   fill_tab<<<148 * 8, 256>>>(tab, tab_max / 8);
   CK(cudaDeviceSynchronize());
+
+  if (argc > 2 && !strcmp(argv[2], "async")) {
+    // C2 point only: LDG (registers + L1 lines) against the cp.async ring, 128-byte slabs and whole 256-byte rows
+    const unsigned nrows = (unsigned)((256L << 20) / 256);
+    fill_idx<<<148 * 8, 256>>>(idx, ng, nrows, 0x5EED0100ull);
+    CK(cudaDeviceSynchronize());
+    run<8, 8>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 8);
+    run<8, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 8);
+    run_async<8, 8, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 4);
+    run_async<8, 12, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 3);
+    run_async<8, 16, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 2);
+    run_async<8, 24, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 2);
+    run_async<8, 48, 4>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 1);
+    run_async<8, 4, 2>("gather128_slab", idx, ng, tab, 128L << 20, 32, out, clk, 8);
+    run<16, 8>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 8);
+    run<16, 4>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 8);
+    run_async<16, 8, 4>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 4);
+    run_async<16, 12, 4>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 3);
+    run_async<16, 24, 4>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 2);
+    run_async<16, 48, 4>("gather256", idx, ng, tab, 256L << 20, 32, out, clk, 1);
+    // L2-resident table: the SM-side ceiling of each path
+    fill_idx<<<148 * 8, 256>>>(idx, ng, (unsigned)((32L << 20) / 256), 0x5EED0101ull);
+    CK(cudaDeviceSynchronize());
+    run<16, 8>("gather256", idx, ng, tab, 32L << 20, 32, out, clk, 8);
+    run_async<16, 12, 4>("gather256", idx, ng, tab, 32L << 20, 32, out, clk, 3);
+    run_async<16, 24, 4>("gather256", idx, ng, tab, 32L << 20, 32, out, clk, 2);
+    return 0;
+  }
   // plain streaming read of the 1 GB table: the DRAM ceiling the gathers are compared with
   {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
