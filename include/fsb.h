@@ -340,7 +340,11 @@ int fsb_tune_csr_staged(int deep);
  * operand repacked into S contiguous column slabs, one pass each); "t_xblock" (1 = x-blocked transpose for A'x with
  * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x); "ata_overlap" (1 = a row shard's A'(A X) partial is produced in four
  * row chunks whose allreduces overlap the next chunk's product, above "ata_overlap_min_kb" KB of partial);
- * multi-GPU block CG: "cg_p2p", "cg_p2p_gram", "cg_p2p_rs", "cg_graph"; "host_x_allgather". */
+ * multi-GPU block CG: "cg_p2p", "cg_p2p_gram", "cg_p2p_rs", "cg_graph"; "host_x_allgather";
+ * "stream_tma" (1, the default: the R = 1 merge-path kernel takes its index / value runs by TMA bulk copies; 0 = per-thread
+ * loads), "stream_tma_minb" (resident CTAs per SM that kernel is built for: 4, 6 (default) or 8); "stream_carveout" /
+ * "staged_carveout" (shared-memory carve-out of the merge-path / staged kernels in percent of the maximum, -1 = the driver's
+ * choice; an explicit value stays in force for the process -- profiles/r2w_l1_carveout.md).  The table holds 16 knobs per thread. */
 int fsb_tune(const char* knob, int value);
 
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable
