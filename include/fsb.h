@@ -344,7 +344,7 @@ int fsb_tune_csr_staged(int deep);
  * "stream_tma" (1, the default: the R = 1 merge-path kernel takes its index / value runs by TMA bulk copies; 0 = per-thread
  * loads), "stream_tma_minb" (resident CTAs per SM that kernel is built for: 4, 6 (default) or 8); "stream_carveout" /
  * "staged_carveout" (shared-memory carve-out of the merge-path / staged kernels in percent of the maximum, -1 = the driver's
- * choice; an explicit value stays in force for the process -- profiles/r2w_l1_carveout.md).  The table holds 16 knobs per thread. */
+ * choice; an explicit value stays in force for the process -- profiles/r2w_l1_carveout.md).  The table holds 32 knobs per thread. */
 int fsb_tune(const char* knob, int value);
 
 /* native = 0 (default): blocked / column-blocked products run the CSR kernels on a row-stable

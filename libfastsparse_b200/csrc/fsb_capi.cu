@@ -44,7 +44,7 @@ int fsb_cuda_error(cudaError_t e, const char* what, const char* file, int line) 
 // experiment knobs: a small per-thread name -> value table (fsb_tune), default from FSB_TUNE_<NAME> in the environment
 namespace {
 struct Knob { char name[32]; int value; };
-thread_local Knob tl_knobs[16];
+thread_local Knob tl_knobs[32];
 thread_local int tl_nknobs = 0;
 }  // namespace
 
@@ -57,7 +57,7 @@ int fsb_knob(const char* name, int dflt) {
   env[k] = 0;
   const char* e = getenv(env);
   const int v = e ? atoi(e) : dflt;
-  if (tl_nknobs < 16) {   // remember (also caches the environment lookup)
+  if (tl_nknobs < 32) {   // remember (also caches the environment lookup)
     snprintf(tl_knobs[tl_nknobs].name, sizeof tl_knobs[0].name, "%s", name);
     tl_knobs[tl_nknobs++].value = v;
   }
@@ -68,7 +68,7 @@ extern "C" int fsb_tune(const char* knob, int value) {
   if (!knob || !*knob || strlen(knob) >= sizeof tl_knobs[0].name) return fsb_set_error(FSB_EINVAL, "fsb_tune: bad knob name");
   for (int i = 0; i < tl_nknobs; ++i)
     if (!strcmp(tl_knobs[i].name, knob)) { tl_knobs[i].value = value; return FSB_OK; }
-  if (tl_nknobs >= 16) return fsb_set_error(FSB_EINVAL, "fsb_tune: knob table full");
+  if (tl_nknobs >= 32) return fsb_set_error(FSB_EINVAL, "fsb_tune: knob table full");
   snprintf(tl_knobs[tl_nknobs].name, sizeof tl_knobs[0].name, "%s", knob);
   tl_knobs[tl_nknobs++].value = value;
   return FSB_OK;

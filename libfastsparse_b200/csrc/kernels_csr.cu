@@ -400,6 +400,10 @@ int fsb_launch_csr_spmm(fsb_matrix* A, double* dY, const double* dX, int R, cuda
       FSB_TRY(max_row_nnz(A, st, &mx));
       stream = mx > std::max(4096.0, 64.0 * A->avg_row_nnz);
     }
+    // binary cell rows of an x-blocked transpose (~67 entries each at C3, x slice L2-resident): the TMA-fed stream kernel,
+    // 0.851 against 0.890 ms for a warp per row (profiles/r2z_binary_t_probe.jsonl); with the whole 80 MB x behind the
+    // gathers the warp-per-row kernel stays ahead (1.04 against 1.26 ms)
+    if (!stream && g_algo == 0 && A->x_live_bytes > 0 && A->avg_row_nnz > 48.0) stream = true;
     if (stream) return stream_config(A, dY, dX, R, st, dZ, lambda);
     if (A->avg_row_nnz <= 48.0) return run_config(A, dY, dX, 1, 2, 1, 1, 2, g_tw, st, dZ, lambda, false);
     return run_config(A, dY, dX, 1, 1, 1, 1, 0, g_tw, st, dZ, lambda);
