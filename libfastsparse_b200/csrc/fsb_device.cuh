@@ -33,6 +33,14 @@ __device__ __forceinline__ unsigned long long make_l2_policy(int kind) {
   unsigned long long p;
   if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  // experiment (knob cap_mult 3xx..6xx of fsb_tune_csr_algo): keep only a FRACTION of the operand's lines (chosen by
+  // address hash) and let the rest stream, for operands about twice the L2 a gather operand gets.  Measured at C2: every
+  // fraction is slower than evict_last 1.0 (4.74-4.96 ms): 0.75 5.05-5.22, 0.5 5.22-5.43, 0.375 5.38-5.49 ms
+  // (profiles/r2z_l2_fraction_probe.jsonl)
+  else if (kind == 3) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(p));
+  else if (kind == 4) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.75;" : "=l"(p));
+  else if (kind == 5) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.375;" : "=l"(p));
+  else if (kind == 6) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(p));
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }

@@ -149,7 +149,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   // the dense operand may be a column slab stored on its own: row stride ldx, first column xcol0
   const double* xbase = X + xcol0 + l * VEC;
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
-  const unsigned long long xpol = make_l2_policy(l2mode ? 1 : 0);
+  const unsigned long long xpol = make_l2_policy(l2mode);   // 1 = evict_last (default), 0 = none, 3..6 = fractional experiments
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
 
   constexpr bool kTma = FSB_STAGED_TMA && (!VALS || FSB_STAGED_TMA_VALS);
@@ -303,7 +303,8 @@ int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, 
 void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
   g_rb = rb;
   g_cap_mult = cap_mult % 100;           // hundreds digit of cap_mult selects the L2 policy experiment:
-  g_l2mode = (cap_mult / 100) == 1 ? 0 : 1;   // 1xx = no cache hints, otherwise X evict_last / stream evict_first
+  const int h = cap_mult / 100;                   // 1xx = no cache hints, 3xx..6xx = fractional evict_last on X (fsb_device.cuh),
+  g_l2mode = h == 1 ? 0 : (h >= 3 && h <= 6) ? h : 1;   // otherwise X evict_last / stream evict_first
 }
 
 // one pass over columns [col0, col0+ncols) with sub-groups of g lanes x vec doubles
