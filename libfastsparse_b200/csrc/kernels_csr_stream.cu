@@ -197,8 +197,8 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
 // ---- R = 1, TMA-fed form (default when the arrays sit on 16-byte boundaries).  The tile's run of column indices and
 // values comes into shared memory by two bulk copies (cp.async.bulk, SASS UBLKCP, completion on one mbarrier, L2
 // evict_first) instead of per-thread LDGs: the matrix stream no longer passes through L1TEX -- whose tag stage the
-// 8-byte gathers saturate (one wavefront per gather, profiles/r2_gather_ceiling.md) -- nor through registers, so the
-// kernel fits 32 registers and eight CTAs per SM.  A run starts at an arbitrary entry: each copy starts at the
+// 8-byte gathers saturate (one wavefront per gather, profiles/r2_gather_ceiling.md) -- nor through registers (40 at six
+// CTAs per SM with all eight gathers of a thread in flight).  A run starts at an arbitrary entry: each copy starts at the
 // enclosing 16-byte boundary and the entries are read at a shift (0..3 indices, 0..1 values).  The row ends share the
 // index buffer (a tile holds kTile merged items: nn entries + ndone row ends), the products overwrite the values in
 // place, so the footprint stays at 24.7 KB per CTA.
