@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
+#include <cub/cub.cuh>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(2); } } while (0)
 
@@ -116,6 +117,111 @@ __global__ void __launch_bounds__(256) gather_q_kernel(const int* __restrict__ i
   if (acc.x + acc.y == 1.2345e300) out[0] = acc.x;
 }
 
+
+// ---- step 3: the whole product, die-affine.  A (fixed 20 entries per row, uniform columns) is split by column half into
+// A0 / A1; persistent CTAs on die 0 run through ALL row blocks with A0 and store the partial rows into Y, CTAs on die 1
+// run through all row blocks with A1, wait for the block's flag and add their sums to what die 0 stored (Y is re-read
+// while still in L2).  Mode 0 is the same kernel on the unsplit matrix with one queue (today's product, minus TMA).
+constexpr int kRB = 128;          // rows per block
+constexpr int kCap = 4096;        // staged indices per block
+template <int U>
+__global__ void __launch_bounds__(256, 5) spmm_q_kernel(int nrow, const int* __restrict__ rp0, const int* __restrict__ c0,
+                                                        const int* __restrict__ rp1, const int* __restrict__ c1,
+                                                        const double* __restrict__ X, double* __restrict__ Y, int col0,
+                                                        const int* __restrict__ die_of_sm, int mode, unsigned long long* ctr,
+                                                        int* ready, int epoch) {
+  __shared__ int s_rp[kRB + 1];
+  __shared__ int s_c[kCap];
+  __shared__ int s_blk;
+  unsigned long long pk;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pk));
+  const int q = mode == 0 ? 0 : die_of_sm[smid()];
+  const int* rp = q ? rp1 : rp0;
+  const int* cc = q ? c1 : c0;
+  const int nblk = (nrow + kRB - 1) / kRB;
+  const int team = threadIdx.x >> 3, l = threadIdx.x & 7;   // 8 lanes x 16 bytes = one 128-byte slab row
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_blk = (int)atomicAdd(ctr + q, 1ull);
+    __syncthreads();
+    const int b = s_blk;
+    if (b >= nblk) break;
+    const int r0 = b * kRB, nr = min(kRB, nrow - r0);
+    for (int i = threadIdx.x; i <= nr; i += 256) s_rp[i] = rp[r0 + i];
+    __syncthreads();
+    const int base = s_rp[0], tot = s_rp[nr] - base;
+    for (int i = threadIdx.x; i < tot && i < kCap; i += 256) s_c[i] = cc[base + i];
+    if (mode == 1 && q == 1 && threadIdx.x == 0) {          // die 1 adds to what die 0 stored for this block
+      int v;
+      do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready + b) : "memory"); } while (v != epoch);
+    }
+    __syncthreads();
+    for (int r = team; r < nr; r += 32) {
+      const int s = s_rp[r] - base, e = s_rp[r + 1] - base;
+      double2 acc = make_double2(0.0, 0.0);
+      for (int i = s; i < e; i += U) {
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          v[u] = make_double2(0.0, 0.0);
+          if (i + u < e) {
+            const int c = s_c[i + u];
+            asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v[u].x), "=d"(v[u].y) : "l"(X + (long)c * 32 + col0 + l * 2), "l"(pk));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+      }
+      double* y = Y + (long)(r0 + r) * 32 + col0 + l * 2;
+      if (mode == 1 && q == 1) {
+        double px, py;
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(px), "=d"(py) : "l"(y) : "memory");
+        acc.x += px; acc.y += py;
+      }
+      asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(y), "d"(acc.x), "d"(acc.y) : "memory");
+    }
+    if (mode == 1 && q == 0) {                               // publish the block's partial rows
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + b), "r"(epoch) : "memory"); }
+    }
+  }
+}
+
+__global__ void gen_cols(int* cols, long nnz, unsigned ncol, unsigned long long seed) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    cols[i] = (int)(((z >> 32) * ncol) >> 32);
+  }
+}
+__global__ void count_lo(const int* cols, int nrow, int deg, int half, int* cnt0, int* cnt1) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  int a = 0;
+  for (int k = 0; k < deg; ++k) a += cols[(long)r * deg + k] < half;
+  cnt0[r] = a; cnt1[r] = deg - a;
+}
+__global__ void split_fill(const int* cols, int nrow, int deg, int half, const int* rp0, const int* rp1, int* c0, int* c1) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrow) return;
+  int a = rp0[r], b = rp1[r];
+  for (int k = 0; k < deg; ++k) { const int c = cols[(long)r * deg + k]; if (c < half) c0[a++] = c; else c1[b++] = c; }
+}
+__global__ void iota_rp(int* rp, int nrow, int deg) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r <= nrow) rp[r] = r * deg;
+}
+__global__ void fill_x(double* x, long n) {   // small integers / 1024: every sum is exact, so the two summation orders agree to the bit
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = (double)((i * 2654435761u) & 1023) / 1024.0;
+}
+__global__ void max_diff(const double* a, const double* b, long n, double* out) {
+  double m = 0.0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmax(m, fabs(a[i] - b[i]));
+  if (m > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
 int main(int argc, char** argv) {
   const long ng = (argc > 1 ? atol(argv[1]) : 200) * 1000000L;
   int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
@@ -186,6 +292,69 @@ int main(int argc, char** argv) {
            label, lpg * 16, table_mb, lpg == 8 ? table_mb / 2 : table_mb, ctas, ng, best, (double)ng * lpg * 16 / (best * 1e-3) / 1e12);
     fflush(stdout);
   };
+
+  // ---- step 3: the product itself
+  if (argc > 2) {
+    int n1 = 0;
+    for (int i = 0; i < nsm; ++i) n1 += die[i];
+    if (n1 < 16 || nsm - n1 < 16) { printf("{\"step\": \"product\", \"skipped\": \"no usable SM -> die map\"}\n"); return 0; }
+    const int nrow = 10000000, ncol = 1000000, deg = 20; const long nnz = (long)nrow * deg;
+    CK(cudaFree(idx0)); CK(cudaFree(idx1)); CK(cudaFree(tab));
+    int *cols, *rpf, *rp0, *rp1, *cnt0, *cnt1, *c0, *c1, *ready; double *X, *Y, *Yref, *dmax;
+    CK(cudaMalloc(&cols, nnz * 4)); CK(cudaMalloc(&rpf, (nrow + 1) * 4L)); CK(cudaMalloc(&rp0, (nrow + 1) * 4L)); CK(cudaMalloc(&rp1, (nrow + 1) * 4L));
+    CK(cudaMalloc(&cnt0, (nrow + 1) * 4L)); CK(cudaMalloc(&cnt1, (nrow + 1) * 4L)); CK(cudaMalloc(&c0, nnz * 4)); CK(cudaMalloc(&c1, nnz * 4));
+    CK(cudaMalloc(&ready, (nrow / kRB + 2) * 4L)); CK(cudaMemset(ready, 0, (nrow / kRB + 2) * 4L));
+    CK(cudaMalloc(&X, (long)ncol * 32 * 8)); CK(cudaMalloc(&Y, (long)nrow * 32 * 8)); CK(cudaMalloc(&Yref, (long)nrow * 32 * 8)); CK(cudaMalloc(&dmax, 8));
+    gen_cols<<<148 * 8, 256>>>(cols, nnz, ncol, 0xC2C2);
+    fill_x<<<148 * 8, 256>>>(X, (long)ncol * 32);
+    iota_rp<<<(nrow + 256) / 256, 256>>>(rpf, nrow, deg);
+    CK(cudaMemset(cnt0, 0, (nrow + 1) * 4L)); CK(cudaMemset(cnt1, 0, (nrow + 1) * 4L));
+    count_lo<<<(nrow + 255) / 256, 256>>>(cols, nrow, deg, ncol / 2, cnt0, cnt1);
+    {
+      void* tmp = nullptr; size_t tb = 0;
+      cub::DeviceScan::ExclusiveSum(tmp, tb, cnt0, rp0, nrow + 1);
+      CK(cudaMalloc(&tmp, tb));
+      cub::DeviceScan::ExclusiveSum(tmp, tb, cnt0, rp0, nrow + 1);
+      cub::DeviceScan::ExclusiveSum(tmp, tb, cnt1, rp1, nrow + 1);
+      CK(cudaFree(tmp));
+    }
+    split_fill<<<(nrow + 255) / 256, 256>>>(cols, nrow, deg, ncol / 2, rp0, rp1, c0, c1);
+    CK(cudaDeviceSynchronize());
+    int epoch = 0;
+    auto product = [&](int mode, double* Yo) {
+      for (int pass = 0; pass < 2; ++pass) {
+        ++epoch;
+        CK(cudaMemsetAsync(ctr, 0, 16));
+        if (mode == 0) spmm_q_kernel<6><<<148 * 5, 256>>>(nrow, rpf, cols, rpf, cols, X, Yo, pass * 16, d_die, 0, ctr, ready, epoch);
+        else spmm_q_kernel<6><<<148 * 5, 256>>>(nrow, rp0, c0, rp1, c1, X, Yo, pass * 16, d_die, 1, ctr, ready, epoch);
+      }
+    };
+    for (int mode : {0, 1, 0, 1}) {
+      double* Yo = mode == 0 ? Yref : Y;
+      product(mode, Yo); product(mode, Yo);
+      CK(cudaDeviceSynchronize());
+      float best = 1e30f;
+      for (int it = 0; it < 4; ++it) {
+        CK(cudaEventRecord(e0));
+        product(mode, Yo);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+      }
+      CK(cudaGetLastError());
+      double hd = 0.0;
+      if (mode == 1) {
+        CK(cudaMemset(dmax, 0, 8));
+        max_diff<<<148 * 8, 256>>>(Y, Yref, (long)nrow * 32, dmax);
+        CK(cudaMemcpy(&hd, dmax, 8, cudaMemcpyDeviceToHost));
+      }
+      printf("{\"step\": \"product\", \"what\": \"binary CSR 10M x 1M, 20 per row, R = 32, two column passes, probe kernel (no TMA staging)\", "
+             "\"assignment\": \"%s\", \"ms\": %.4f, \"max_abs_diff_vs_unsplit\": %.3g}\n",
+             mode == 0 ? "any CTA, whole rows (today)" : "die-affine column halves, die 1 adds to die 0's partial rows", best, hd);
+      fflush(stdout);
+    }
+    return 0;
+  }
   const char* names[4] = {"any CTA, whole table (today)", "die-affine halves", "die-affine, halves swapped", "two queues, CTAs assigned by blockIdx parity (control)"};
   for (int ctas : {5, 8})
     for (long mb : {256L, 128L}) {
