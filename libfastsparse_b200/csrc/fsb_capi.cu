@@ -10,6 +10,7 @@
 #include <atomic>
 #include <math.h>
 #include <mutex>
+#include <stdint.h>
 #include <vector>
 
 #include "fsb_internal.h"
@@ -72,6 +73,40 @@ extern "C" int fsb_tune(const char* knob, int value) {
   snprintf(tl_knobs[tl_nknobs].name, sizeof tl_knobs[0].name, "%s", knob);
   tl_knobs[tl_nknobs++].value = value;
   return FSB_OK;
+}
+
+cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_bytes, cudaStream_t st) {
+  if (!p || texels == 0 || texels > ((size_t)1 << 27) || ((uintptr_t)p & 511) || (texel_bytes != 8 && texel_bytes != 16)) return 0;
+  {   // a captured graph outlives this table: kernels recorded into one keep to plain loads (same bits)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cs != cudaStreamCaptureStatusNone) return 0;
+  }
+  struct Slot { const void* p; size_t n; int b; cudaTextureObject_t t; unsigned long long used; };
+  static thread_local Slot tab[16] = {};
+  static thread_local unsigned long long clock = 0;
+  ++clock;
+  Slot* lru = &tab[0];
+  for (auto& s : tab) {
+    if (s.t && s.p == p && s.n == texels && s.b == texel_bytes) { s.used = clock; return s.t; }
+    if (s.used < lru->used) lru = &s;
+  }
+  if (lru->t) {   // a product launched with this object may still be running on st
+    cudaStreamSynchronize(st);
+    cudaDestroyTextureObject(lru->t);
+    *lru = Slot{};
+  }
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypeLinear;
+  rd.res.linear.devPtr = const_cast<void*>(p);
+  rd.res.linear.desc = texel_bytes == 8 ? cudaCreateChannelDesc<int2>() : cudaCreateChannelDesc<int4>();
+  rd.res.linear.sizeInBytes = texels * (size_t)texel_bytes;
+  cudaTextureDesc td = {};
+  td.readMode = cudaReadModeElementType;
+  cudaTextureObject_t t = 0;
+  if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  *lru = Slot{p, texels, texel_bytes, t, clock};
+  return t;
 }
 
 void fsb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -79,6 +79,12 @@ cudaStream_t fsb_default_stream();
 void fsb_count_launch(int n = 1);
 // experiment knob (per calling thread; fsb_tune sets it, FSB_TUNE_<NAME> in the environment is the default)
 int fsb_knob(const char* name, int dflt);
+// Linear texture object over a device buffer of `texels` elements of 8 (int2) or 16 (int4) bytes, for gathers through
+// the texture pipe (tex1Dfetch): its data stage is separate from the LSU's, which shared-memory traffic also uses
+// (profiles/r2z_tex_gathers.md).  Objects are descriptors only (no ownership of the buffer); a small per-thread table
+// keeps them, the least recently used one is destroyed after a synchronise of `st`.  Returns 0 when the buffer does not
+// qualify (512-byte alignment, <= 2^27 texels) or the object cannot be created: callers fall back to plain loads.
+cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_bytes, cudaStream_t st);
 
 #define FSB_CUDA(call)                                                        \
   do {                                                                        \

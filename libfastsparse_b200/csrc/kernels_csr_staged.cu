@@ -85,11 +85,27 @@ template <> __device__ __forceinline__ void pin_after_loads<4>(double (&x)[4]) {
   asm volatile("" : "+d"(x[0]), "+d"(x[1]), "+d"(x[2]), "+d"(x[3]));
 }
 
+// gather of VEC doubles at element offset `off` (doubles) through a linear texture of 8-byte (VEC = 1) or 16-byte texels
+template <int VEC> __device__ __forceinline__ void tex_gather(double (&v)[VEC], cudaTextureObject_t t, int off);
+template <> __device__ __forceinline__ void tex_gather<1>(double (&v)[1], cudaTextureObject_t t, int off) {
+  const int2 w = tex1Dfetch<int2>(t, off);
+  v[0] = __hiloint2double(w.y, w.x);
+}
+template <> __device__ __forceinline__ void tex_gather<2>(double (&v)[2], cudaTextureObject_t t, int off) {
+  const int4 w = tex1Dfetch<int4>(t, off >> 1);
+  v[0] = __hiloint2double(w.y, w.x); v[1] = __hiloint2double(w.w, w.z);
+}
+template <> __device__ __forceinline__ void tex_gather<4>(double (&v)[4], cudaTextureObject_t t, int off) {
+  const int4 a = tex1Dfetch<int4>(t, off >> 1), b = tex1Dfetch<int4>(t, (off >> 1) + 1);
+  v[0] = __hiloint2double(a.y, a.x); v[1] = __hiloint2double(a.w, a.z);
+  v[2] = __hiloint2double(b.y, b.x); v[3] = __hiloint2double(b.w, b.z);
+}
+
 // One row, summed strictly in stored order, gathers issued in batches of U.
-template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP>
+template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP, bool TEX>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
                                          double (&acc)[VEC], const double* __restrict__ xbase, int ldx, bool col_ok,
-                                         unsigned long long xpol) {
+                                         unsigned long long xpol, cudaTextureObject_t xtex, int xoff) {
   constexpr int U = VALS ? FSB_STAGED_U_VALS : FSB_STAGED_U;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
@@ -100,7 +116,8 @@ __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const doubl
       if (idx < e && col_ok) {
         const int c = FROM_SMEM ? ci[idx] : __ldg(ci + idx);
         if (VALS) vv[u] = FROM_SMEM ? vi[idx] : __ldg(vi + idx);
-        XLoad<VEC>::ldp(xr[u], xbase + (long long)c * ldx, xpol);
+        if (TEX) tex_gather<VEC>(xr[u], xtex, c * ldx + xoff);
+        else XLoad<VEC>::ldp(xr[u], xbase + (long long)c * ldx, xpol);
       } else {
         if (VALS) vv[u] = 0.0;
 #pragma unroll
@@ -126,11 +143,11 @@ __device__ __forceinline__ void add_scaled_row(double (&acc)[VEC], const double*
   for (int v = 0; v < VEC; ++v) acc[v] = fma(lambda, __ldg(Z + off + v), acc[v]);
 }
 
-template <int G, int VEC, bool VALS, bool DEEP>
+template <int G, int VEC, bool VALS, bool DEEP, bool TEX>
 __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                                             int R, int col0, int ncols, int RB, int CAP, int l2mode,
-                                            const double* __restrict__ Z, double lambda, int ldx, int xcol0) {
+                                            const double* __restrict__ Z, double lambda, int ldx, int xcol0, cudaTextureObject_t xtex) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -148,6 +165,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   const bool col_ok = l * VEC < ncols;
   // the dense operand may be a column slab stored on its own: row stride ldx, first column xcol0
   const double* xbase = X + xcol0 + l * VEC;
+  const int xoff = xcol0 + l * VEC;                 // the same offset in doubles, for the texture form of the gather
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
   const unsigned long long xpol = make_l2_policy(l2mode);   // 1 = evict_last (default), 0 = none, 3..6 = fractional experiments
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
@@ -190,7 +208,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true, DEEP>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol);
+      walk_row<G, VEC, VALS, true, DEEP, TEX>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -211,7 +229,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, cs, ce, acc, xbase, ldx, col_ok, xpol);
+      walk_row<G, VEC, VALS, false, DEEP, TEX>(cols, vals, cs, ce, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -231,7 +249,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP>(cols, vals, s, e, acc, xbase, ldx, col_ok, xpol);
+      walk_row<G, VEC, VALS, false, DEEP, TEX>(cols, vals, s, e, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -241,25 +259,26 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   }
 }
 
-template <int G, int VEC, bool VALS>
+template <int G, int VEC, bool VALS, bool TEX>
 __global__ void __launch_bounds__(kThreads)
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                        int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
-                       int ldx, int xcol0) {
-  staged_body<G, VEC, VALS, false>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0);
+                       int ldx, int xcol0, cudaTextureObject_t xtex) {
+  staged_body<G, VEC, VALS, false, TEX>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
 }
 
-template <int G, int VEC, bool VALS>
+template <int G, int VEC, bool VALS, bool TEX>
 __global__ void __launch_bounds__(kThreads, VALS ? FSB_STAGED_DEEP_MINB_VALS : FSB_STAGED_DEEP_MINB)
 csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                             int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
-                            int ldx, int xcol0) {
-  staged_body<G, VEC, VALS, true>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0);
+                            int ldx, int xcol0, cudaTextureObject_t xtex) {
+  staged_body<G, VEC, VALS, true, TEX>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
 }
 
 thread_local int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
+thread_local bool g_use_tex = false;   // set per launch by fsb_launch_csr_spmm_staged
 
 template <int G, int VEC, bool VALS>
 int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, int ncols, int RB, int CAP, cudaStream_t st,
@@ -268,16 +287,30 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
   // (every array the library allocates does)
   if (FSB_STAGED_TMA && (!VALS || FSB_STAGED_TMA_VALS) && ((uintptr_t)A->cols & 15))
     return fsb_set_error(FSB_EINVAL, "staged SpMM: column index array is not 16-byte aligned");
-  auto kern = deep ? csr_spmm_staged_deep_kernel<G, VEC, VALS> : csr_spmm_staged_kernel<G, VEC, VALS>;
+  // gathers through a linear texture over the dense operand (knob "staged_tex": 1 = on, 0 = off; default: narrow
+  // operands, see fsb_launch_csr_spmm_staged).  No L2 policy word exists for texture fetches, so operands that rely on
+  // evict_last (the half-resident 256 MB operand of C2) keep the LDG form.
+  cudaTextureObject_t xtex = 0;
+  if (g_use_tex) {
+    const size_t xd = (size_t)A->ncol * (size_t)ldx;            // doubles in the operand (or its repacked slab)
+    const double* xorigin = dX;                                   // texel 0; gathers add c * ldx + xcol0 + l * VEC doubles
+    if (xd + 32 < ((size_t)1 << 31) && (VEC == 1 || (ldx % 2 == 0 && xcol0 % 2 == 0)))
+      xtex = fsb_linear_texture(xorigin, VEC == 1 ? xd : xd / 2, VEC == 1 ? 8 : 16, st);
+  }
   size_t body = std::max((size_t)(CAP + 16) * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging (+ alignment / vector-read slack) or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
-  if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {   // experiment knob: shared-memory carve-out in percent of the maximum (-1: the driver's choice)
-    const int co = fsb_knob("staged_carveout", -1);
-    if (co >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-  }
   const unsigned grid = (unsigned)((A->nrow + RB - 1) / RB);
-  kern<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, ldx, xcol0);
+  const int co = fsb_knob("staged_carveout", -1);   // experiment knob: shared-memory carve-out in percent of the maximum (-1: the driver's choice)
+#define FSB_STAGED_GO(KERN_)                                                                                                  \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(KERN_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    if (co >= 0) cudaFuncSetAttribute(KERN_, cudaFuncAttributePreferredSharedMemoryCarveout, co);                             \
+    KERN_<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, \
+                                        ldx, xcol0, xtex);                                                                    \
+  } while (0)
+  if (xtex) { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, true>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, true>)); }
+  else      { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, false>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, false>)); }
+#undef FSB_STAGED_GO
   return FSB_OK;
 }
 
@@ -300,6 +333,15 @@ int launch_g(int vec, const fsb_matrix* A, double* dY, const double* dX, int R, 
 
 }  // namespace
 
+// where the texture form of the gather is the default (profiles/r2z_tex_gathers.md)
+// binary SpMV and R = 2 / 4 gain 1.4-2 % (0.752 -> 0.741, 0.764 -> 0.753, 0.816 -> 0.800 ms at C3's structure); gathers of
+// 64 bytes and more per row lose 20-40 % (R = 8: 1.07 -> 1.29 ms, C4 R = 32: 3.25 -> 4.33 ms, C2: 5.18 -> 6.10 ms), and so
+// do matrices with values on this kernel
+static bool staged_tex_auto(const fsb_matrix* A, int R, int ncols, int vec) {
+  (void)ncols; (void)vec;
+  return !A->has_vals && R <= 4;
+}
+
 void fsb_csr_staged_set_tuning(int rb, int cap_mult) {
   g_rb = rb;
   g_cap_mult = cap_mult % 100;           // hundreds digit of cap_mult selects the L2 policy experiment:
@@ -321,6 +363,10 @@ int fsb_launch_csr_spmm_staged(const fsb_matrix* A, double* dY, const double* dX
   rb = std::max(rb, 1);
   int cap = (int)std::min<double>(avg * rb * (g_cap_mult ? g_cap_mult : 1.5) + 256, 3.0 * budget);
   cap = std::max((cap + 63) & ~63, 512);
+  {   // texture-pipe gathers: knob "staged_tex" 1 = always, 0 = never, -1 (default) = where measured faster
+    const int kt = fsb_knob("staged_tex", -1);
+    g_use_tex = kt == 1 || (kt < 0 && staged_tex_auto(A, R, ncols, vec));
+  }
   int rc;
   switch (g) {
     case 1: rc = launch_g<1>(vec, A, dY, dX, R, col0, ncols, rb, cap, st, dZ, lambda, deep, ldx, xcol0); break;
