@@ -934,14 +934,46 @@ def test_stream_kernel_tma_fed_form_is_bit_identical_to_the_per_thread_load_form
     fs.check(L.fsb_tune_csr_algo(3, 0, 0))
     try:
         got = {}
-        for form in (1, 0):
-            fs.check(L.fsb_tune(b"stream_tma", form))
+        for form in (1, 0, 2):       # 2 = the TMA-fed form with LDG gathers instead of texture fetches (knob stream_tex)
+            fs.check(L.fsb_tune(b"stream_tma", 1 if form else 0)); fs.check(L.fsb_tune(b"stream_tex", 0 if form == 2 else 1))
             got[form] = (M.spmm(x, 1).cpu().numpy(), M.spmm_t(xt, 1).cpu().numpy())
     finally:
-        fs.check(L.fsb_tune(b"stream_tma", 1)); fs.check(L.fsb_tune_csr_algo(0, 0, 0))
+        fs.check(L.fsb_tune(b"stream_tma", 1)); fs.check(L.fsb_tune(b"stream_tex", 1)); fs.check(L.fsb_tune_csr_algo(0, 0, 0))
     assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    assert np.array_equal(got[2][0], got[1][0]) and np.array_equal(got[2][1], got[1][1])
     want = oracle.csr_mul(nrow, rp, cc, vv, tvec(ncol).reshape(-1, 1), 1).reshape(-1)
     sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(tvec(ncol)).reshape(-1, 1), 1)).reshape(-1)
     assert_close(got[1][0], want, sc, what="TMA-fed stream kernel vs oracle")
     want_t = oracle.coo_mul(nrow, rows, cols, v, tvec(nrow), transpose=True, ncol=ncol)
     assert_close(got[1][1], want_t, scale=2.0 * float(np.bincount(cols, minlength=ncol).max()), what="TMA-fed stream kernel, transpose, vs oracle")
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 8, 32, 100])
+def test_staged_kernel_texture_gathers_give_the_same_bits(R):
+    """Knob staged_tex: the staged kernel fetches the dense operand through a linear texture (8-byte texels for one
+    double per lane, 16-byte texels for two or four) instead of LDG -- the default for binary matrices with R <= 4
+    (kernels_csr_staged.cu staged_tex_auto).  Same bits as the LDG form on a ragged matrix with empty rows and a row
+    long enough for the split path, with and without values, A x and the cached transpose."""
+    import torch
+    rng = np.random.default_rng(100 + R)
+    nrow, ncol, nnz = 3001, 777, 40000
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=5000)
+    L = fs.lib()
+    X = torch.from_numpy(f64(rng.standard_normal((ncol, R)))).cuda().reshape(-1)
+    Xt = torch.from_numpy(f64(rng.standard_normal((nrow, R)))).cuda().reshape(-1)
+    for v in (None, vals):
+        M = fs.DeviceMatrix.from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(),
+                                             torch.from_numpy(v).cuda() if v is not None else None)
+        fs.check(L.fsb_tune_csr_algo(2, 0, 0))
+        try:
+            got = {}
+            for tex in (0, 1):
+                fs.check(L.fsb_tune(b"staged_tex", tex))
+                got[tex] = (M.spmm(X, R).cpu().numpy(), M.spmm_t(Xt, R).cpu().numpy())
+        finally:
+            fs.check(L.fsb_tune(b"staged_tex", -1)); fs.check(L.fsb_tune_csr_algo(0, 0, 0))
+        assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1]), f"R={R} vals={v is not None}"
+        rp, cc, vv = oracle.csr_from_coo(nrow, rows, cols, v)
+        Xh = X.cpu().numpy().reshape(ncol, R)
+        sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(Xh), R)).reshape(-1)
+        assert_close(got[1][0], oracle.csr_mul(nrow, rp, cc, vv, Xh, R), sc, what=f"texture gathers R={R} vals={v is not None}")
