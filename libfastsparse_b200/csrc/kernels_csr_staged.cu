@@ -102,11 +102,12 @@ template <> __device__ __forceinline__ void tex_gather<4>(double (&v)[4], cudaTe
 }
 
 // One row, summed strictly in stored order, gathers issued in batches of U.
-template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP, bool TEX>
+template <int G, int VEC, bool VALS, bool FROM_SMEM, bool DEEP, int MODE>
 __device__ __forceinline__ void walk_row(const int* __restrict__ ci, const double* __restrict__ vi, int s, int e,
                                          double (&acc)[VEC], const double* __restrict__ xbase, int ldx, bool col_ok,
                                          unsigned long long xpol, cudaTextureObject_t xtex, int xoff) {
   constexpr int U = VALS ? FSB_STAGED_U_VALS : FSB_STAGED_U;
+  constexpr bool TEX = MODE == 1;
   for (int i = s; i < e; i += U) {
     double xr[U][VEC];
     double vv[U];
@@ -143,7 +144,7 @@ __device__ __forceinline__ void add_scaled_row(double (&acc)[VEC], const double*
   for (int v = 0; v < VEC; ++v) acc[v] = fma(lambda, __ldg(Z + off + v), acc[v]);
 }
 
-template <int G, int VEC, bool VALS, bool DEEP, bool TEX>
+template <int G, int VEC, bool VALS, bool DEEP, int MODE>
 __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                                             int R, int col0, int ncols, int RB, int CAP, int l2mode,
@@ -208,7 +209,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, true, DEEP, TEX>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
+      walk_row<G, VEC, VALS, true, DEEP, MODE>(ci, vi, s_rp[r] - base, s_rp[r + 1] - base, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -229,7 +230,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP, TEX>(cols, vals, cs, ce, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
+      walk_row<G, VEC, VALS, false, DEEP, MODE>(cols, vals, cs, ce, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) s_red[(team * G + l) * VEC + v] = acc[v];
       __syncthreads();
@@ -249,7 +250,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
       double acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
-      walk_row<G, VEC, VALS, false, DEEP, TEX>(cols, vals, s, e, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
+      walk_row<G, VEC, VALS, false, DEEP, MODE>(cols, vals, s, e, acc, xbase, ldx, col_ok, xpol, xtex, xoff);
       if (col_ok) {
         const long long off = (long long)(r0 + r) * R + col0 + l * VEC;
         add_scaled_row<VEC>(acc, Z, lambda, off);
@@ -259,22 +260,22 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   }
 }
 
-template <int G, int VEC, bool VALS, bool TEX>
+template <int G, int VEC, bool VALS, int MODE>
 __global__ void __launch_bounds__(kThreads)
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                        int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
                        int ldx, int xcol0, cudaTextureObject_t xtex) {
-  staged_body<G, VEC, VALS, false, TEX>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
+  staged_body<G, VEC, VALS, false, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
 }
 
-template <int G, int VEC, bool VALS, bool TEX>
+template <int G, int VEC, bool VALS, int MODE>
 __global__ void __launch_bounds__(kThreads, VALS ? FSB_STAGED_DEEP_MINB_VALS : FSB_STAGED_DEEP_MINB)
 csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                             int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
                             int ldx, int xcol0, cudaTextureObject_t xtex) {
-  staged_body<G, VEC, VALS, true, TEX>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
+  staged_body<G, VEC, VALS, true, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
 }
 
 thread_local int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
@@ -308,8 +309,11 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
     KERN_<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, \
                                         ldx, xcol0, xtex);                                                                    \
   } while (0)
-  if (xtex) { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, true>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, true>)); }
-  else      { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, false>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, false>)); }
+  // MODE: 0 = LDG gathers, 1 = texture gathers.  (A mode 2 -- column indices by one LDS per chunk of entries + warp shuffles
+  // instead of one broadcast LDS per gather, to take the index reads off the LSU data pipe -- was measured and removed:
+  // C4 3.03 -> 4.70 ms, C2 5.00 -> 6.62 ms, profiles/r2z_idx_shfl_probe.jsonl.)
+  if (xtex) { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, 1>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, 1>)); }
+  else      { if (deep) FSB_STAGED_GO((csr_spmm_staged_deep_kernel<G, VEC, VALS, 0>)); else FSB_STAGED_GO((csr_spmm_staged_kernel<G, VEC, VALS, 0>)); }
 #undef FSB_STAGED_GO
   return FSB_OK;
 }
