@@ -82,13 +82,15 @@ cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_b
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return 0; }
     if (cs != cudaStreamCaptureStatusNone) return 0;
   }
-  struct Slot { const void* p; size_t n; int b; cudaTextureObject_t t; unsigned long long used; };
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  struct Slot { const void* p; size_t n; int b; int dev; cudaTextureObject_t t; unsigned long long used; };
   static thread_local Slot tab[16] = {};
   static thread_local unsigned long long clock = 0;
   ++clock;
   Slot* lru = &tab[0];
   for (auto& s : tab) {
-    if (s.t && s.p == p && s.n == texels && s.b == texel_bytes) { s.used = clock; return s.t; }
+    if (s.t && s.p == p && s.n == texels && s.b == texel_bytes && s.dev == dev) { s.used = clock; return s.t; }
     if (s.used < lru->used) lru = &s;
   }
   if (lru->t) {   // a product launched with this object may still be running on st
@@ -105,7 +107,7 @@ cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_b
   td.readMode = cudaReadModeElementType;
   cudaTextureObject_t t = 0;
   if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
-  *lru = Slot{p, texels, texel_bytes, t, clock};
+  *lru = Slot{p, texels, texel_bytes, dev, t, clock};
   return t;
 }
 
