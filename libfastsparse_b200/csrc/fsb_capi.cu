@@ -75,8 +75,14 @@ extern "C" int fsb_tune(const char* knob, int value) {
   return FSB_OK;
 }
 
-cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_bytes, cudaStream_t st) {
-  if (!p || texels == 0 || texels > ((size_t)1 << 27) || ((uintptr_t)p & 511) || (texel_bytes != 8 && texel_bytes != 16)) return 0;
+cudaTextureObject_t fsb_linear_texture(const void* p_in, size_t texels_in, int texel_bytes, cudaStream_t st, int* texel_off) {
+  *texel_off = 0;
+  if (!p_in || texels_in == 0 || (texel_bytes != 8 && texel_bytes != 16) || ((uintptr_t)p_in % (uintptr_t)texel_bytes)) return 0;
+  const uintptr_t lead = (uintptr_t)p_in & 511;                      // bytes between the 512-byte boundary below and p
+  const void* p = (const void*)((uintptr_t)p_in - lead);
+  const size_t texels = texels_in + lead / (size_t)texel_bytes;
+  if (texels > ((size_t)1 << 27)) return 0;
+  *texel_off = (int)(lead / (size_t)texel_bytes);
   {   // a captured graph outlives this table: kernels recorded into one keep to plain loads (same bits)
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -82,9 +82,11 @@ int fsb_knob(const char* name, int dflt);
 // Linear texture object over a device buffer of `texels` elements of 8 (int2) or 16 (int4) bytes, for gathers through
 // the texture pipe (tex1Dfetch): its data stage is separate from the LSU's, which shared-memory traffic also uses
 // (profiles/r2z_tex_gathers.md).  Objects are descriptors only (no ownership of the buffer); a small per-thread table
-// keeps them, the least recently used one is destroyed after a synchronise of `st`.  Returns 0 when the buffer does not
-// qualify (512-byte alignment, <= 2^27 texels) or the object cannot be created: callers fall back to plain loads.
-cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_bytes, cudaStream_t st);
+// keeps them, the least recently used one is destroyed after a synchronise of `st`.  A linear texture must start on a
+// 512-byte boundary: the object starts at the boundary at or below p and *texel_off receives the index of p's first texel
+// in it (add it to every fetch index).  Returns 0 when the buffer does not qualify (p not texel-aligned, more than 2^27
+// texels) or the object cannot be created: callers fall back to plain loads.
+cudaTextureObject_t fsb_linear_texture(const void* p, size_t texels, int texel_bytes, cudaStream_t st, int* texel_off);
 
 #define FSB_CUDA(call)                                                        \
   do {                                                                        \

@@ -148,7 +148,7 @@ template <int G, int VEC, bool VALS, bool DEEP, int MODE>
 __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                                             int R, int col0, int ncols, int RB, int CAP, int l2mode,
-                                            const double* __restrict__ Z, double lambda, int ldx, int xcol0, cudaTextureObject_t xtex) {
+                                            const double* __restrict__ Z, double lambda, int ldx, int xcol0, cudaTextureObject_t xtex, int xtex_off) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: [row_ptr: RB+1 ints, padded to 16 B] [vals: CAP doubles (VALS)] [cols: CAP ints];
   // the long-row reduction buffer (kThreads*VEC doubles) aliases the vals/cols region
@@ -166,7 +166,7 @@ __device__ __forceinline__ void staged_body(int nrow, const int* __restrict__ ro
   const bool col_ok = l * VEC < ncols;
   // the dense operand may be a column slab stored on its own: row stride ldx, first column xcol0
   const double* xbase = X + xcol0 + l * VEC;
-  const int xoff = xcol0 + l * VEC;                 // the same offset in doubles, for the texture form of the gather
+  const int xoff = xtex_off + xcol0 + l * VEC;      // the same offset in doubles (from the texture's first texel), for the texture form of the gather
   // l2mode 1: dense operand evict_last, matrix stream evict_first (keep X resident in L2)
   const unsigned long long xpol = make_l2_policy(l2mode);   // 1 = evict_last (default), 0 = none, 3..6 = fractional experiments
   const unsigned long long spol = make_l2_policy(l2mode ? 2 : 0);
@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(kThreads)
 csr_spmm_staged_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                        const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                        int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
-                       int ldx, int xcol0, cudaTextureObject_t xtex) {
-  staged_body<G, VEC, VALS, false, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
+                       int ldx, int xcol0, cudaTextureObject_t xtex, int xtex_off) {
+  staged_body<G, VEC, VALS, false, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex, xtex_off);
 }
 
 template <int G, int VEC, bool VALS, int MODE>
@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, VALS ? FSB_STAGED_DEEP_MINB_VALS : F
 csr_spmm_staged_deep_kernel(int nrow, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                             const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                             int R, int col0, int ncols, int RB, int CAP, int l2mode, const double* __restrict__ Z, double lambda,
-                            int ldx, int xcol0, cudaTextureObject_t xtex) {
-  staged_body<G, VEC, VALS, true, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex);
+                            int ldx, int xcol0, cudaTextureObject_t xtex, int xtex_off) {
+  staged_body<G, VEC, VALS, true, MODE>(nrow, row_ptr, cols, vals, X, Y, R, col0, ncols, RB, CAP, l2mode, Z, lambda, ldx, xcol0, xtex, xtex_off);
 }
 
 thread_local int g_rb = 0, g_cap_mult = 0, g_l2mode = 1;
@@ -292,11 +292,13 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
   // operands, see fsb_launch_csr_spmm_staged).  No L2 policy word exists for texture fetches, so operands that rely on
   // evict_last (the half-resident 256 MB operand of C2) keep the LDG form.
   cudaTextureObject_t xtex = 0;
+  int xtex_off = 0;   // first texel of the operand in the texture (which starts on the 512-byte boundary below it), in doubles
   if (g_use_tex) {
     const size_t xd = (size_t)A->ncol * (size_t)ldx;            // doubles in the operand (or its repacked slab)
     const double* xorigin = dX;                                   // texel 0; gathers add c * ldx + xcol0 + l * VEC doubles
     if (xd + 32 < ((size_t)1 << 31) && (VEC == 1 || (ldx % 2 == 0 && xcol0 % 2 == 0)))
-      xtex = fsb_linear_texture(xorigin, VEC == 1 ? xd : xd / 2, VEC == 1 ? 8 : 16, st);
+      xtex = fsb_linear_texture(xorigin, VEC == 1 ? xd : xd / 2, VEC == 1 ? 8 : 16, st, &xtex_off);
+    if (VEC != 1) xtex_off *= 2;
   }
   size_t body = std::max((size_t)(CAP + 16) * (VALS ? 12 : 4), (size_t)kThreads * VEC * 8);   // staging (+ alignment / vector-read slack) or long-row reduction
   size_t smem = ((((size_t)RB + 1) * 4 + 15) & ~(size_t)15) + ((body + 15) & ~(size_t)15);
@@ -307,7 +309,7 @@ int launch(const fsb_matrix* A, double* dY, const double* dX, int R, int col0, i
     if (smem > 48 * 1024) FSB_CUDA(cudaFuncSetAttribute(KERN_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     if (co >= 0) cudaFuncSetAttribute(KERN_, cudaFuncAttributePreferredSharedMemoryCarveout, co);                             \
     KERN_<<<grid, kThreads, smem, st>>>(A->nrow, A->row_ptr, A->cols, A->vals, dX, dY, R, col0, ncols, RB, CAP, g_l2mode, dZ, lambda, \
-                                        ldx, xcol0, xtex);                                                                    \
+                                        ldx, xcol0, xtex, xtex_off);                                                          \
   } while (0)
   // MODE: 0 = LDG gathers, 1 = texture gathers.  (A mode 2 -- column indices by one LDS per chunk of entries + warp shuffles
   // instead of one broadcast LDS per gather, to take the index reads off the LSU data pipe -- was measured and removed:

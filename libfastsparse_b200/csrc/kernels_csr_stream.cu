@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 csr_stream_tma_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, const int* __restrict__ cols,
                       const double* __restrict__ vals, const double* __restrict__ X, double* __restrict__ Y,
                       const int* __restrict__ split, int* __restrict__ carry_row, double* __restrict__ carry_val,
-                      cudaTextureObject_t xtex) {
+                      cudaTextureObject_t xtex, int xtex_off) {
   constexpr int kTile = Tile<1>::n;
   __shared__ __align__(16) int s_ci[kTile + 16];      // [index run from the 16-byte boundary | row ends]
   __shared__ __align__(16) double s_pv[kTile + 4];    // values in, products out (same slots)
@@ -247,7 +247,7 @@ csr_stream_tma_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, 
       xv[p] = 0.0;
       if (t < nn) {
         if (TEX) {   // the gather through the texture pipe: its data stage is not the LSU's, which the shared-memory traffic shares
-          const int2 w = tex1Dfetch<int2>(xtex, s_ci[shc + t]);
+          const int2 w = tex1Dfetch<int2>(xtex, s_ci[shc + t] + xtex_off);
           xv[p] = __hiloint2double(w.y, w.x);
         } else {
           xv[p] = __ldg(X + s_ci[shc + t]);
@@ -313,12 +313,13 @@ int launch(fsb_matrix* A, double* dY, const double* dX, cudaStream_t st) {
     // gathers through a linear texture over x (knob "stream_tex", default on): the texture pipe's data stage is not the
     // LSU's, which this kernel's shared-memory traffic saturates together with the gathers (LSU data pipe 83 % busy):
     // C3 double SpMV 0.909 -> 0.800 ms, A'x 0.920 -> 0.814 ms, same bits (profiles/r2z_tex_gathers.md)
-    const cudaTextureObject_t xtex = fsb_knob("stream_tex", 1) ? fsb_linear_texture(dX, (size_t)A->ncol, 8, st) : 0;
+    int xtex_off = 0;
+    const cudaTextureObject_t xtex = fsb_knob("stream_tex", 1) ? fsb_linear_texture(dX, (size_t)A->ncol, 8, st, &xtex_off) : 0;
 #define FSB_TMA_LAUNCH2(MINB_, TEX_)                                                                                         \
   do {                                                                                                                       \
     if (co >= 0) cudaFuncSetAttribute(csr_stream_tma_kernel<VALS, MINB_, TEX_>, cudaFuncAttributePreferredSharedMemoryCarveout, co); \
     csr_stream_tma_kernel<VALS, MINB_, TEX_><<<ntiles, kThreads, 0, st>>>(A->nrow, A->nnz, A->row_ptr, A->cols, A->vals, dX, dY, A->split, \
-                                                                          carry_row, carry_val, xtex);                       \
+                                                                          carry_row, carry_val, xtex, xtex_off);                       \
   } while (0)
 #define FSB_TMA_LAUNCH(MINB_) do { if (xtex) FSB_TMA_LAUNCH2(MINB_, true); else FSB_TMA_LAUNCH2(MINB_, false); } while (0)
     if (minb >= 8) FSB_TMA_LAUNCH(8); else if (minb <= 4) FSB_TMA_LAUNCH(4); else FSB_TMA_LAUNCH(6);

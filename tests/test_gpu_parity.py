@@ -977,3 +977,34 @@ def test_staged_kernel_texture_gathers_give_the_same_bits(R):
         Xh = X.cpu().numpy().reshape(ncol, R)
         sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(Xh), R)).reshape(-1)
         assert_close(got[1][0], oracle.csr_mul(nrow, rp, cc, vv, Xh, R), sc, what=f"texture gathers R={R} vals={v is not None}")
+
+
+@pytest.mark.parametrize("offset", [1, 2, 37])
+def test_texture_gathers_from_operands_off_the_512_byte_boundary(offset):
+    """A linear texture must start on a 512-byte boundary; operands that do not (a row shard's slice of a larger vector)
+    get a texture from the boundary below plus a texel offset (fsb_capi.cu fsb_linear_texture).  Products with the dense
+    operand `offset` doubles into an allocation: texture and LDG forms agree to the bit, R = 1 (merge-path kernel,
+    matrix with values) and R = 1, 2, 4 (staged kernel, binary)."""
+    import torch
+    rng = np.random.default_rng(offset)
+    nrow, ncol, nnz = 4001, 1500, 50000
+    rows, cols, vals = _random_case(rng, nrow, ncol, nnz, long_row=3000)
+    L = fs.lib()
+    Md = fs.DeviceMatrix.from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), torch.from_numpy(vals).cuda())
+    Mb = fs.DeviceMatrix.from_coo_tensors(nrow, ncol, torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), None)
+    for M, R, knob in ((Md, 1, b"stream_tex"), (Mb, 1, b"staged_tex"), (Mb, 2, b"staged_tex"), (Mb, 4, b"staged_tex")):
+        big = torch.from_numpy(f64(rng.standard_normal(ncol * R + 64))).cuda()
+        X = big[offset:offset + ncol * R]
+        assert X.data_ptr() % 512 != 0
+        got = {}
+        try:
+            for tex in (1, 0):
+                fs.check(L.fsb_tune(knob, tex))
+                got[tex] = M.spmm(X, R).cpu().numpy()
+        finally:
+            fs.check(L.fsb_tune(b"stream_tex", 1)); fs.check(L.fsb_tune(b"staged_tex", -1))
+        assert np.array_equal(got[0], got[1]), f"R={R} offset={offset}"
+        rp, cc, vv = oracle.csr_from_coo(nrow, rows, cols, vals if M is Md else None)
+        Xh = X.cpu().numpy().reshape(ncol, R)
+        sc = np.abs(oracle.csr_mul(nrow, rp, cc, np.abs(vv) if vv is not None else None, np.abs(Xh), R)).reshape(-1)
+        assert_close(got[1], oracle.csr_mul(nrow, rp, cc, vv, Xh, R), sc, what=f"offset operand R={R}")
