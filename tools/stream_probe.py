@@ -1,6 +1,7 @@
 """C3 double SpMV / transposed SpMV with the merge-path stream kernel under a list of knob settings (one process, one
 matrix): which form of the kernel (per-thread loads or TMA-fed), how many resident CTAs per SM (= how much of the
-256 KB is left to L1 for outstanding gather misses), gathers with or without L1 allocation.
+256 KB is left to L1 for outstanding gather misses), gathers by LDG or through the texture pipe.  (The run recorded in
+profiles/r2w_stream_probe.jsonl also had a gathers-with-L1::no_allocate setting, removed from the kernel since.)
 
     python tools/stream_probe.py [--small] [--out gpurun_out/stream_probe.jsonl]
 """
@@ -19,17 +20,15 @@ from tools.bench_all import timed  # noqa: E402
 
 SETTINGS = [
     {"stream_tma": 0},
-    {"stream_tma": 0, "stream_x_na": 1},
-    {"stream_tma": 1, "stream_tma_minb": 8},
-    {"stream_tma": 1, "stream_tma_minb": 6},
-    {"stream_tma": 1, "stream_tma_minb": 5},
-    {"stream_tma": 1, "stream_tma_minb": 4},
-    {"stream_tma": 1, "stream_tma_minb": 8, "stream_x_na": 1},
-    {"stream_tma": 1, "stream_tma_minb": 6, "stream_x_na": 1},
-    {"stream_tma": 1, "stream_tma_minb": 5, "stream_x_na": 1},
-    {"stream_tma": 1, "stream_tma_minb": 4, "stream_x_na": 1},
+    {"stream_tma": 1, "stream_tma_minb": 8, "stream_tex": 0},
+    {"stream_tma": 1, "stream_tma_minb": 6, "stream_tex": 0},
+    {"stream_tma": 1, "stream_tma_minb": 4, "stream_tex": 0},
+    {"stream_tma": 1, "stream_tma_minb": 8, "stream_tex": 1},
+    {"stream_tma": 1, "stream_tma_minb": 6, "stream_tex": 1},
+    {"stream_tma": 1, "stream_tma_minb": 4, "stream_tex": 1},
 ]
-ALL = ("stream_tma", "stream_tma_minb", "stream_x_na")
+ALL = ("stream_tma", "stream_tma_minb", "stream_tex")
+DEFAULTS = {"stream_tma": 1, "stream_tma_minb": 6, "stream_tex": 1}
 
 
 def main():
@@ -50,7 +49,7 @@ def main():
         yref = zref = None
         for s in SETTINGS:
             for k in ALL:
-                fs.check(L.fsb_tune(k.encode(), s.get(k, {"stream_tma": 1, "stream_tma_minb": 8, "stream_x_na": 0}[k])))
+                fs.check(L.fsb_tune(k.encode(), s.get(k, DEFAULTS[k])))
             ms = timed(lambda: A.spmm(x, 1, out=y), args.reps)
             mt = timed(lambda: A.spmm_t(y, 1, out=z), args.reps) if with_vals else None
             if yref is None:
@@ -61,6 +60,8 @@ def main():
             if out:
                 out.write(json.dumps(line) + "\n"); out.flush()
         fs.check(L.fsb_tune_csr_algo(0, 0, 0))
+        for k in ALL:
+            fs.check(L.fsb_tune(k.encode(), DEFAULTS[k]))
         del A
 
 
