@@ -338,7 +338,7 @@ int fsb_tune_csr_staged(int deep);
  * FSB_TUNE_<NAME> gives the default).  Known knobs: "stream_policy" (1 = L2 evict_first on the matrix
  * stream / evict_last on the dense operand in the merge-path kernel, 0 = plain loads, the default); "x_slabs" (S >= 2: the dense
  * operand repacked into S contiguous column slabs, one pass each); "t_xblock" (1 = x-blocked transpose for A'x with
- * one right-hand side when x exceeds "t_xblock_min_kb" KB, blocks of "t_xblock_kb" KB of x); "ata_overlap" (1 = a row shard's A'(A X) partial is produced in four
+ * one right-hand side when x exceeds "t_xblock_min_kb" KB -- 0, the default, means the built-in 52 MB for matrices with values and 36 MB for binary ones -- blocks of "t_xblock_kb" KB of x); "ata_overlap" (1 = a row shard's A'(A X) partial is produced in four
  * row chunks whose allreduces overlap the next chunk's product, above "ata_overlap_min_kb" KB of partial);
  * multi-GPU block CG: "cg_p2p", "cg_p2p_gram", "cg_p2p_rs", "cg_graph"; "host_x_allgather";
  * "stream_tma" (1, the default: the R = 1 merge-path kernel takes its index / value runs by TMA bulk copies; 0 = per-thread

@@ -519,7 +519,13 @@ static int spmm_t_overlapped_allreduce(fsb_matrix* A, double* dY, const double* 
 }
 
 static bool use_xblocked_t(const fsb_matrix* A, int R) {
-  return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > ((size_t)fsb_knob("t_xblock_min_kb", 36 << 10) << 10) && fsb_knob("t_xblock", 1);
+  // Threshold: 36 MB measured with LDG gathers (profiles/r2p_xblock_threshold.jsonl).  With the texture-pipe gathers the plain
+  // transpose of a matrix with values stays ahead up to a 48 MB operand (0.480 against 0.494 ms) and loses from 64 MB
+  // (0.802 against 0.653 ms): 52 MB there (profiles/r2z_xblock_threshold.jsonl); binary matrices keep 36 MB.  The knob, when
+  // set, applies to both.
+  const int min_kb = fsb_knob("t_xblock_min_kb", 0);
+  const size_t min_bytes = min_kb > 0 ? (size_t)min_kb << 10 : (A->has_vals ? (size_t)52 << 20 : (size_t)36 << 20);
+  return R == 1 && A->ncol > 0 && (size_t)A->nrow * 8 > min_bytes && fsb_knob("t_xblock", 1);
 }
 
 extern "C" {

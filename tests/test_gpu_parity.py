@@ -800,7 +800,7 @@ def test_xblocked_transposed_spmv_matches_the_plain_transpose(with_vals):
         blocked = M.spmm_t(xd, 1).cpu().numpy()
         z = M.ata(torch.from_numpy(tvec(ncol)).cuda(), 1, lam=0.5).cpu().numpy()
     finally:
-        fs.check(L.fsb_tune(b"t_xblock_min_kb", 36 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
+        fs.check(L.fsb_tune(b"t_xblock_min_kb", 0)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))   # 0 = the built-in thresholds
     want = oracle.coo_mul(nrow, rows, cols, vals, x, transpose=True, ncol=ncol)
     scale = 2.0 * float(np.bincount(cols, minlength=ncol).max())
     assert_close(blocked, want, scale=scale, what="x-blocked A'x vs oracle")
@@ -911,7 +911,7 @@ def test_round2_paths_on_degenerate_inputs():
         M0 = fs.DeviceMatrix.from_coo_tensors(nrow, 5, z[:0], z[:0], None)
         assert not M0.spmm_t(x, 1).cpu().numpy().any()
     finally:
-        fs.check(L.fsb_tune(b"t_xblock_min_kb", 36 << 10)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))
+        fs.check(L.fsb_tune(b"t_xblock_min_kb", 0)); fs.check(L.fsb_tune(b"t_xblock_kb", 32 << 10))   # 0 = the built-in thresholds
 
 
 @pytest.mark.parametrize("with_vals", [False, True])
