@@ -140,7 +140,6 @@ csr_stream_kernel(int nrow, long long nnz, const int* __restrict__ row_ptr, cons
   __shared__ int s_end[kTile + 1];
   __shared__ double s_p[kTile * RT];
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
   const long long total = (long long)nrow + nnz;
   const long long d0 = (long long)blockIdx.x * kTile;
   const long long d1 = min(d0 + kTile, total);
